@@ -1,0 +1,93 @@
+/*
+ * tair_b200 — C ABI of the B200-native TeReDiff patch-denoising hot path.
+ *
+ * This is the drop-in boundary: every entry point takes plain device pointers,
+ * explicit sizes and a cudaStream_t (passed as void*), enqueues work on that
+ * stream without synchronising, and returns 0 on success or a negative code
+ * (the message is available from tair_last_error()).  Outputs are always
+ * caller-allocated.  There is no CPU fallback: a missing / unloadable library
+ * is a hard error on the Python side (tair_b200/_lib.py).
+ *
+ * Reference interfaces replaced (paths relative to the yinnhao/TAIR tree):
+ *   - testr/adet/layers/csrc/vision.cpp:52-55, DeformAttn/ms_deform_attn.h:20-40
+ *       `_C.ms_deform_attn_forward`                      -> tair_msda_forward
+ *   - terediff/sampler/spaced_sampler.py:141-147,123-131,167-189 (p_sample math)
+ *                                                        -> tair_sampler_update
+ *   - val_patches.py:114-206 (merge_patches_with_overlap) -> tair_blend_tiles
+ *   - terediff/model/unet.py:203-223 / util.py:182-193 (GroupNorm32+SiLU)
+ *                                                        -> tair_groupnorm_nhwc
+ *   - terediff/model/attention.py:252-254 (nn.LayerNorm) -> tair_layernorm
+ *   - nn.Linear / 1x1 nn.Conv2d call sites (attention.py:181-186,206,301-331;
+ *     unet.py:170-176,189-197; controlnet.py:318-321)    -> tair_gemm_bf16
+ *   - 3x3 nn.Conv2d call sites (unet.py:67,99,152,178; controlnet.py:168-175)
+ *                                                        -> tair_conv3x3_bf16
+ *   - F.scaled_dot_product_attention (attention.py:206)  -> tair_attention_bf16
+ *
+ * Layout convention: activations are channels-last bf16, i.e. a (B,C,H,W)
+ * reference tensor is held as a row-major [B*H*W, C] matrix.  Weights are
+ * repacked once at load time to [Cout, K] bf16 with K contiguous
+ * (K = Cin for linear/1x1, K = 9*Cin ordered (ky,kx,ci) for 3x3).
+ */
+#ifndef TAIR_B200_H_
+#define TAIR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAIR_OK 0
+#define TAIR_ERR_INVALID (-1)
+#define TAIR_ERR_CUDA (-2)
+#define TAIR_ERR_UNSUPPORTED (-3)
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* tair_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int tair_abi_version(void);
+/* Number of kernel launches issued through this library by the calling process
+ * since load (or since the last reset).  bench.py reports it as gpu_launches. */
+int64_t tair_launch_count(void);
+void tair_launch_count_reset(void);
+
+/* ---- epilogue shared by the tensor-core GEMM and the implicit-GEMM conv ---- */
+enum {
+  TAIR_ACT_NONE = 0,
+  TAIR_ACT_GEGLU = 1, /* out[:, j] = v[:, j] * gelu(g[:, j]); weight rows tile-interleaved, see DESIGN.md */
+  TAIR_ACT_GELU = 2,
+  TAIR_ACT_SILU = 3,
+  TAIR_ACT_RELU = 4
+};
+
+typedef struct tair_epilogue {
+  void* out;               /* [M, ldc] bf16 (or fp32 when out_fp32 != 0)              */
+  int64_t ldc;             /* elements between consecutive output rows                 */
+  int32_t out_fp32;        /* 0: bf16 output, 1: fp32 output                           */
+  int32_t act;             /* TAIR_ACT_*; applied after bias / row-group add           */
+  const float* bias;       /* [N] fp32 or NULL                                         */
+  const void* residual;    /* [M, ldr] bf16 added after the activation, or NULL        */
+  int64_t ldr;
+  const float* rowgroup;   /* [ceil(M/rows_per_group), ldg] fp32 added before act, or NULL
+                              (timestep-embedding add: one row per image)              */
+  int64_t ldg;
+  int32_t rows_per_group;
+  int32_t reserved;
+} tair_epilogue;
+
+/* out = epilogue(A[M,K] * W[N,K]^T).  A, W bf16, K contiguous; lda/ldw in elements
+ * (multiples of 8).  fp32 accumulation in tensor memory (tcgen05). */
+int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
+                   int32_t K, const tair_epilogue* epi, void* stream);
+
+/* 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM:
+ *   x  [B, H, W, Cin] bf16 channels-last (Cin % 64 == 0)
+ *   w  [Cout, 9*Cin]  bf16, K ordered (ky, kx, ci)
+ *   out rows are output pixels in (b, ho, wo) order; M = B*Ho*Wo, N = Cout. */
+int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                      int32_t Cout, int32_t stride, const tair_epilogue* epi, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAIR_B200_H_ */

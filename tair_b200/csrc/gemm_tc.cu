@@ -1,0 +1,485 @@
+// Tensor-core GEMM and implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] * W[N,K]^T )          bf16 x bf16 -> fp32 (TMEM) -> bf16/fp32
+//
+// Replaces the nn.Linear / nn.Conv2d call sites of the reference UNet/ControlNet/TESTR
+// (terediff/model/unet.py:152,170-197; attention.py:181-186,206,301-331;
+//  controlnet.py:168-175,318-321; testr/adet/modeling/testr/models.py:76-88).
+//
+// Design (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0      TMA producer : cp.async.bulk.tensor -> 128B-swizzled smem ring (STAGES deep)
+//   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block
+//   warp 2      TMEM owner   : allocates 2 x BN fp32 accumulator columns (double buffered)
+//   warps 4..7  epilogue     : tcgen05.ld 32x32b -> bias / timestep-row add / activation /
+//                              residual -> 16-byte stores; overlaps the next tile's mainloop
+// For the 3x3 convolution the A operand is never materialised: the producer walks the
+// 9 filter taps x Cin/64 channel blocks and issues a 4-D TMA box load on the NHWC
+// activation with shifted (w,h) start coordinates; TMA's out-of-bounds zero fill implements
+// the padding and elementStrides implements stride 2.
+#include <atomic>
+
+#include "../../include/tair_b200.h"
+#include "common.cuh"
+
+namespace tair {
+
+extern std::atomic<int64_t> g_launch_count;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr uint32_t A_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, num_kb;
+  int conv;        // 0 plain, 1 conv3x3
+  int kb_per_tap;  // Cin / 64
+  int Ho, Wo, stride;
+  int vec_out, vec_res;
+  tair_epilogue epi;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 160) ? 6 : ((BN >= 128) ? 6 : 8));
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (ACT == TAIR_ACT_GELU) return gelu_f(x);
+  else if constexpr (ACT == TAIR_ACT_SILU) return silu_f(x);
+  else if constexpr (ACT == TAIR_ACT_RELU) return fmaxf(x, 0.f);
+  else return x;
+}
+
+// one thread: NC consecutive output columns [n, n+NC) of row m, values in v[]
+template <int NC>
+__device__ __forceinline__ void epi_finish_store(const GemmParams& p, int m, int n, int ncols_total,
+                                                 float (&v)[NC]) {
+  const tair_epilogue& e = p.epi;
+  const bool full = (n + NC <= ncols_total);
+  if (e.residual != nullptr) {
+    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + (int64_t)m * e.ldr + n;
+    if (full && p.vec_res) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+        float2 f0 = unpack_bf16(q.x), f1 = unpack_bf16(q.y), f2 = unpack_bf16(q.z), f3 = unpack_bf16(q.w);
+        v[j + 0] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+        v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n + j < ncols_total) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (e.out_fp32) {
+    float* op = reinterpret_cast<float*>(e.out) + (int64_t)m * e.ldc + n;
+    if (full && p.vec_out) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4)
+        *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n + j < ncols_total) op[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(e.out) + (int64_t)m * e.ldc + n;
+    if (full && p.vec_out) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        uint4 q;
+        q.x = pack_bf16(v[j + 0], v[j + 1]);
+        q.y = pack_bf16(v[j + 2], v[j + 3]);
+        q.z = pack_bf16(v[j + 4], v[j + 5]);
+        q.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(op + j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n + j < ncols_total) op[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+// Drain one 128 x BN accumulator tile: this thread owns output row m (TMEM lane = row in tile).
+// Templated on the activation so that each executed path is a compact straight-line loop
+// (a runtime switch per element blew the instruction cache and throttled the epilogue ~10x).
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn, bool row_ok, uint32_t taddr) {
+  const tair_epilogue& e = p.epi;
+      const float* rg = nullptr;
+      if (e.rowgroup != nullptr && row_ok) rg = e.rowgroup + (int64_t)(m / e.rows_per_group) * e.ldg;
+
+      if constexpr (ACT == TAIR_ACT_GEGLU) {
+        constexpr int HALF = BN / 2;
+        const int nout_total = p.N / 2;
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 16) {
+          uint32_t rv[16], rgt[16];
+          tmem_ld_32x16(taddr + c, rv);
+          tmem_ld_32x16(taddr + HALF + c, rgt);
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[16];
+            const int nv = tn * BN + c;          // row index (in the interleaved W) of the value part
+            const int ng = tn * BN + HALF + c;   // ... and of the gate part
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(rv[j]);
+              float g = __uint_as_float(rgt[j]);
+              if (e.bias != nullptr) {
+                a += __ldg(e.bias + nv + j);
+                g += __ldg(e.bias + ng + j);
+              }
+              v[j] = a * gelu_f(g);
+            }
+            epi_finish_store<16>(p, m, tn * HALF + c, nout_total, v);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          const int n = tn * BN + c;
+          if (row_ok && n < p.N) {
+            float v[32];
+            if (n + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = __uint_as_float(r[j]);
+                if (e.bias != nullptr) a += __ldg(e.bias + n + j);
+                if (rg != nullptr) a += __ldg(rg + n + j);
+                v[j] = apply_act<ACT>(a);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = __uint_as_float(r[j]);
+                if (n + j < p.N) {
+                  if (e.bias != nullptr) a += __ldg(e.bias + n + j);
+                  if (rg != nullptr) a += __ldg(rg + n + j);
+                }
+                v[j] = apply_act<ACT>(a);
+              }
+            }
+            epi_finish_store<32>(p, m, n, p.N, v);
+          }
+        }
+      }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int m0 = tm * BM, n0 = tn * BN;
+        int img = 0, ho0 = 0, wo0 = 0;
+        if (p.conv) {
+          const int hw = p.Ho * p.Wo;
+          img = m0 / hw;
+          const int rem = m0 - img * hw;
+          ho0 = rem / p.Wo;
+          wo0 = rem - ho0 * p.Wo;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          if (!p.conv) {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m0);
+          } else {
+            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * BK, wo0 * p.stride + dx - 1,
+                        ho0 * p.stride + dy - 1, img);
+          }
+          tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const tair_epilogue& e = p.epi;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m = tm * BM + ew * 32 + lane;
+      const bool row_ok = m < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+      switch (e.act) {
+        case TAIR_ACT_GEGLU: epilogue_tile<BN, TAIR_ACT_GEGLU>(p, m, tn, row_ok, taddr); break;
+        case TAIR_ACT_GELU: epilogue_tile<BN, TAIR_ACT_GELU>(p, m, tn, row_ok, taddr); break;
+        case TAIR_ACT_SILU: epilogue_tile<BN, TAIR_ACT_SILU>(p, m, tn, row_ok, taddr); break;
+        case TAIR_ACT_RELU: epilogue_tile<BN, TAIR_ACT_RELU>(p, m, tn, row_ok, taddr); break;
+        default: epilogue_tile<BN, TAIR_ACT_NONE>(p, m, tn, row_ok, taddr); break;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TAIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("gemm_tc_kernel");
+}
+
+// Cycles per K=16 step of one 128xBN tile: the larger of the tensor-pipe floor
+// (128*BN/256) and the shared-memory operand read (A 4 KB + B BN*32 B at 128 B/clk).
+int tile_cost(int bn) {
+  int mma = bn / 2, smem = 32 + bn / 4;
+  return mma > smem ? mma : smem;
+}
+
+int pick_bn(int M, int N, int act) {
+  if (act == TAIR_ACT_GEGLU) return (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 0);
+  const int cands[4] = {256, 160, 128, 64};
+  const int tiles_m = (M + BM - 1) / BM;
+  const int sms = num_sms();
+  long best = -1;
+  int best_bn = 128;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long cost = waves * tile_cost(bn);
+    if (best < 0 || cost < best) {
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn,
+             cudaStream_t st) {
+  CUtensorMap tmB;
+  const uint64_t dimsB[2] = {(uint64_t)p.K, (uint64_t)p.N};
+  const uint64_t strB[1] = {(uint64_t)ldw * 2};
+  const uint32_t boxB[2] = {BK, (uint32_t)bn};
+  int rc = make_tmap_bf16(&tmB, W, 2, dimsB, strB, boxB, nullptr, true);
+  if (rc) return rc;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + bn - 1) / bn;
+  switch (bn) {
+    case 256: return launch_bn<256>(tmA, tmB, p, st);
+    case 160: return launch_bn<160>(tmA, tmB, p, st);
+    case 128: return launch_bn<128>(tmA, tmB, p, st);
+    case 64: return launch_bn<64>(tmA, tmB, p, st);
+  }
+  set_error("gemm: unsupported BN %d", bn);
+  return TAIR_ERR_UNSUPPORTED;
+}
+
+int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
+  TAIR_REQUIRE(e != nullptr && e->out != nullptr, "epilogue/out pointer is NULL");
+  TAIR_REQUIRE(e->ldc >= n_out, "ldc (%lld) < output columns (%d)", (long long)e->ldc, n_out);
+  TAIR_REQUIRE(e->act >= 0 && e->act <= TAIR_ACT_RELU, "unknown activation %d", e->act);
+  if (e->rowgroup) TAIR_REQUIRE(e->rows_per_group > 0, "rows_per_group must be > 0");
+  if (e->act == TAIR_ACT_GEGLU)
+    TAIR_REQUIRE(e->rowgroup == nullptr, "GEGLU epilogue does not take a row-group add");
+  p.epi = *e;
+  const int esz = e->out_fp32 ? 4 : 2;
+  p.vec_out = ((reinterpret_cast<uintptr_t>(e->out) % 16) == 0) && ((e->ldc * esz) % 16 == 0);
+  p.vec_res = e->residual && ((reinterpret_cast<uintptr_t>(e->residual) % 16) == 0) &&
+              ((e->ldr * 2) % 16 == 0);
+  return TAIR_OK;
+}
+
+}  // namespace
+}  // namespace tair
+
+using namespace tair;
+
+extern "C" int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M,
+                              int32_t N, int32_t K, const tair_epilogue* epi, void* stream) {
+  TAIR_REQUIRE(A && W, "gemm: NULL operand");
+  TAIR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  TAIR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K,
+               "gemm: lda/ldw must be >= K and multiples of 8 (lda=%lld ldw=%lld K=%d)",
+               (long long)lda, (long long)ldw, K);
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(A) % 16) == 0 && (reinterpret_cast<uintptr_t>(W) % 16) == 0,
+               "gemm: operands must be 16-byte aligned");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_kb = (K + BK - 1) / BK;
+  p.conv = 0;
+  const int act = epi ? epi->act : 0;
+  const int n_out = (act == TAIR_ACT_GEGLU) ? N / 2 : N;
+  int rc = check_epilogue(epi, p, n_out);
+  if (rc) return rc;
+  const int bn = pick_bn(M, N, act);
+  TAIR_REQUIRE(bn != 0, "gemm: GEGLU epilogue needs N %% 128 == 0 (N=%d)", N);
+  CUtensorMap tmA;
+  const uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M};
+  const uint64_t strA[1] = {(uint64_t)lda * 2};
+  const uint32_t boxA[2] = {BK, BM};
+  rc = make_tmap_bf16(&tmA, A, 2, dimsA, strA, boxA, nullptr, true);
+  if (rc) return rc;
+  return dispatch(tmA, W, ldw, p, bn, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_t H, int32_t W,
+                                 int32_t Cin, int32_t Cout, int32_t stride, const tair_epilogue* epi,
+                                 void* stream) {
+  TAIR_REQUIRE(x && w, "conv3x3: NULL operand");
+  TAIR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: bad shape");
+  TAIR_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2 (got %d)", stride);
+  TAIR_REQUIRE(Cin % 64 == 0, "conv3x3: Cin must be a multiple of 64 (got %d)", Cin);
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(w) % 16) == 0,
+               "conv3x3: operands must be 16-byte aligned");
+  // PyTorch conv arithmetic, k=3, pad=1
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  // An M tile is 128 consecutive output pixels = bn images x bh rows x bw columns.
+  const int bw = Wo < BM ? Wo : BM;
+  TAIR_REQUIRE(BM % bw == 0 && Wo % bw == 0, "conv3x3: output width %d does not tile 128", Wo);
+  int bh = BM / bw;
+  if (bh > Ho) bh = Ho;
+  TAIR_REQUIRE(Ho % bh == 0 && BM % (bw * bh) == 0, "conv3x3: output height %d does not tile 128", Ho);
+  const int bimg = BM / (bw * bh);
+  TAIR_REQUIRE(bimg == 1 || bh == Ho, "conv3x3: internal tiling error");
+  TAIR_REQUIRE(bw * stride <= 256 && bh * stride <= 256, "conv3x3: TMA box too large");
+
+  GemmParams p{};
+  p.M = B * Ho * Wo; p.N = Cout; p.K = 9 * Cin;
+  p.num_kb = 9 * (Cin / BK);
+  p.conv = 1; p.kb_per_tap = Cin / BK;
+  p.Ho = Ho; p.Wo = Wo; p.stride = stride;
+  const int act = epi ? epi->act : 0;
+  TAIR_REQUIRE(act != TAIR_ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
+  int rc = check_epilogue(epi, p, Cout);
+  if (rc) return rc;
+  const int bn = pick_bn(p.M, p.N, act);
+
+  CUtensorMap tmA;
+  const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strA[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  const uint32_t boxA[4] = {BK, (uint32_t)(bw * stride), (uint32_t)(bh * stride), (uint32_t)bimg};
+  const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  rc = make_tmap_bf16(&tmA, x, 4, dimsA, strA, boxA, es, true);
+  if (rc) return rc;
+  return dispatch(tmA, w, (int64_t)9 * Cin, p, bn, static_cast<cudaStream_t>(stream));
+}
