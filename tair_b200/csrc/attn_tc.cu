@@ -1,0 +1,306 @@
+// Flash-style attention for sm_100a, head_dim 64, no mask (UNet self/cross attention).
+//
+// Replaces F.scaled_dot_product_attention at terediff/model/attention.py:206
+// (SDPCrossAttention.forward :189-216): softmax(Q K^T * scale) V per (batch, head).
+//
+// One CTA = one (batch, head, 128-query tile); two CTAs are co-resident per SM so that one
+// CTA's softmax (CUDA cores / MUFU) overlaps the other's tensor-core work.
+//   warp 0       TMA producer: Q once, then K/V blocks of 128 keys into a 2-stage ring
+//   warp 1       TMEM owner + MMA issuer: S = Q K^T (M128 N128 K64) and O_j = P V (M128 N64 K128)
+//   warps 2..5   softmax: one thread per query row; S read with tcgen05.ld, running max / sum in
+//                registers, P written as bf16 into 128B-swizzled smem (the A operand of P V),
+//                per-block O_j read back from TMEM and accumulated (with rescale) in registers
+// TMEM (256 columns): S fp32 [0,128) | O_j double buffer [128,192) [192,256).
+#include <atomic>
+#include <math_constants.h>
+
+#include "../../include/tair_b200.h"
+#include "common.cuh"
+
+namespace tair {
+extern std::atomic<int64_t> g_launch_count;
+namespace {
+
+constexpr int AT_BM = 128;   // queries per CTA
+constexpr int AT_BN = 128;   // keys per block
+constexpr int AT_D = 64;     // head dim
+constexpr int AT_THREADS = 192;
+constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // 16 KB: one 128-row x 64-col bf16 tile
+constexpr uint32_t SM_Q = 0;
+constexpr uint32_t SM_K = SM_Q + TILE_BYTES;          // 2 stages
+constexpr uint32_t SM_V = SM_K + 2 * TILE_BYTES;      // 2 stages
+constexpr uint32_t SM_P = SM_V + 2 * TILE_BYTES;      // 2 k-atoms of 16 KB
+constexpr uint32_t SM_BAR = SM_P + 2 * TILE_BYTES;
+constexpr uint32_t AT_SMEM = SM_BAR + 128;
+constexpr uint32_t AT_TMEM_COLS = 256;
+
+struct AttnParams {
+  int B, H, Lq, Lk;
+  int q_tiles, nblk;
+  float scale_log2;  // scale * log2(e)
+  __nv_bfloat16* o;
+  int64_t ldo;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + SM_BAR;
+  const uint32_t q_full = bar + 0;
+  const uint32_t s_full = bar + 8;
+  const uint32_t p_full = bar + 16;
+  auto kv_full = [&](int s) { return bar + 24 + 8u * s; };
+  auto kv_empty = [&](int s) { return bar + 40 + 8u * s; };
+  auto o_full = [&](int b) { return bar + 56 + 8u * b; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qt * AT_BM;
+
+  if (threadIdx.x == 0) {
+    if ((sbase & 1023u) != 0) __trap();  // swizzle-128B tiles need 1024-byte alignment
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+      mbar_init(o_full(s), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tm_S = tmem;
+  const uint32_t tm_O = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sbase + SM_Q, &tmQ, q_full, h * AT_D, q0, b);
+      for (int j = 0; j < p.nblk; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
+        tma_load_3d(sbase + SM_K + s * TILE_BYTES, &tmK, kv_full(s), h * AT_D, j * AT_BN, b);
+        tma_load_3d(sbase + SM_V + s * TILE_BYTES, &tmV, kv_full(s), h * AT_D, j * AT_BN, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S: A=Q K-major, B=K K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // O: A=P K-major, B=V MN-major
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(kv_full(s), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = sbase + SM_Q, ka = sbase + SM_K + s * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_ss(tm_S, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024),
+                  idesc_s, k != 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < p.nblk; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t pa = sbase + SM_P, va = sbase + SM_V + s * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k)
+          umma_ss(tm_O + s * 64, umma_desc_sw128(pa + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(va + k * 2048, 16, 1024), idesc_o, k != 0);
+        umma_commit(o_full(s));
+        umma_commit(kv_empty(s));
+        if (j + 1 < p.nblk) issue_s(j + 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;       // query row inside the tile
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float o[AT_D];
+#pragma unroll
+    for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+    float m_run = -CUDART_INF_F, l_run = 0.f;
+    const float c = p.scale_log2;
+    uint8_t* prow = smem + SM_P + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < p.nblk; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
+      // pass 1: row max
+      float mx = -CUDART_INF_F;
+#pragma unroll 1
+      for (int cc = 0; cc < AT_BN; cc += 32) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tm_S + lane_off + cc, sv);
+        tmem_ld_wait();
+        if (kvalid >= cc + 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc + i < kvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * c);
+      // fold in the previous block's P V (ready once its MMA retired; also frees the P buffer)
+      if (j > 0) {
+        const int pb = (j - 1) & 1;
+        mbar_wait(o_full(pb), ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tm_O + lane_off + pb * 64 + half * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[half * 32 + i] += __uint_as_float(ov[i]);
+        }
+      }
+      const float alpha = exp2f(m_run - m_new);
+#pragma unroll
+      for (int i = 0; i < AT_D; ++i) o[i] *= alpha;
+      l_run *= alpha;
+      // pass 2: P = exp2(S*c - m_new) -> bf16 -> swizzled smem ; row sum
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < AT_BN; cc += 32) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tm_S + lane_off + cc, sv);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = exp2f(fmaf(__uint_as_float(sv[i]), c, -m_new));
+          if (cc + i >= kvalid) e = 0.f;
+          pv[i] = e;
+          lsum += e;
+        }
+        // 32 columns = 4 chunks of 16 B; chunk index inside the 64-wide k-atom is XOR-swizzled by row
+        uint8_t* atom = prow + (cc >> 6) * TILE_BYTES;
+        const int chunk0 = (cc & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]);
+          w.y = pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]);
+          w.z = pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]);
+          w.w = pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) = w;
+        }
+      }
+      l_run += lsum;
+      m_run = m_new;
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // last block's P V
+    {
+      const int pb = (p.nblk - 1) & 1;
+      mbar_wait(o_full(pb), ((p.nblk - 1) >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tm_O + lane_off + pb * 64 + half * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[half * 32 + i] += __uint_as_float(ov[i]);
+      }
+    }
+    const int q = q0 + r;
+    if (q < p.Lq) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* op = p.o + ((int64_t)b * p.Lq + q) * p.ldo + h * AT_D;
+#pragma unroll
+      for (int i = 0; i < AT_D; i += 8) {
+        uint4 w;
+        w.x = pack_bf16(o[i + 0] * inv, o[i + 1] * inv);
+        w.y = pack_bf16(o[i + 2] * inv, o[i + 3] * inv);
+        w.z = pack_bf16(o[i + 4] * inv, o[i + 5] * inv);
+        w.w = pack_bf16(o[i + 6] * inv, o[i + 7] * inv);
+        *reinterpret_cast<uint4*>(op + i) = w;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, AT_TMEM_COLS);
+  }
+}
+
+int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int B) {
+  const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)L, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
+  const uint32_t box[3] = {AT_D, 128, 1};
+  return make_tmap_bf16(m, base, 3, dims, str, box, nullptr, true);
+}
+
+}  // namespace
+}  // namespace tair
+
+using namespace tair;
+
+extern "C" int tair_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                   int64_t ldv, void* o, int64_t ldo, int32_t B, int32_t H, int32_t Lq,
+                                   int32_t Lk, int32_t head_dim, float scale, void* stream) {
+  TAIR_REQUIRE(q && k && v && o, "attention: NULL pointer");
+  TAIR_REQUIRE(head_dim == 64, "attention: tensor-core path is built for head_dim 64 (got %d)", head_dim);
+  TAIR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attention: bad shape");
+  TAIR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+               "attention: row strides must be multiples of 8 elements");
+  TAIR_REQUIRE(ldq >= H * 64 && ldk >= H * 64 && ldv >= H * 64 && ldo >= H * 64,
+               "attention: row stride smaller than H*head_dim");
+  for (const void* ptr : {q, k, v, (const void*)o})
+    TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention: pointers must be 16-byte aligned");
+  AttnParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.q_tiles = (Lq + AT_BM - 1) / AT_BM;
+  p.nblk = (Lk + AT_BN - 1) / AT_BN;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_map(&tmQ, q, ldq, H * 64, Lq, B))) return rc;
+  if ((rc = make_map(&tmK, k, ldk, H * 64, Lk, B))) return rc;
+  if ((rc = make_map(&tmV, v, ldv, H * 64, Lk, B))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TAIR_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    attr_set = true;
+  }
+  const long grid = (long)B * H * p.q_tiles;
+  TAIR_REQUIRE(grid < (1l << 31), "attention: grid too large");
+  attn_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("attn_tc_kernel");
+}

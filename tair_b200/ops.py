@@ -119,3 +119,28 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.lib().tair_launch_count_reset()
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, H: int, Lq: int, Lk: int,
+              head_dim: int = 64, scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v per (batch, head).
+
+    q [B*Lq, >=H*D], k/v [B*Lk, >=H*D] are 2-D bf16 views with unit inner stride (column slices of a fused
+    projection buffer are fine); head h lives in columns [h*D, (h+1)*D).  Returns [B*Lq, H*D] bf16.
+    """
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _cuda(t, n, BF16)
+    q2, ldq = _rows(q, "q")
+    k2, ldk = _rows(k, "k")
+    v2, ldv = _rows(v, "v")
+    if q2.shape[0] != B * Lq or k2.shape[0] != B * Lk or v2.shape[0] != B * Lk:
+        raise TairError("attention: row counts do not match B*Lq / B*Lk")
+    if out is None:
+        out = torch.empty((B * Lq, H * head_dim), device=q.device, dtype=BF16)
+    o2, ldo = _rows(out, "out")
+    if scale is None:
+        scale = head_dim ** -0.5
+    rc = _lib.lib().tair_attention_bf16(q2.data_ptr(), ldq, k2.data_ptr(), ldk, v2.data_ptr(), ldv, o2.data_ptr(), ldo,
+                                        B, H, Lq, Lk, head_dim, float(scale), _stream())
+    _lib.check(rc, "tair_attention_bf16")
+    return out
