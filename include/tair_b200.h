@@ -94,6 +94,57 @@ int tair_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, 
                         void* o, int64_t ldo, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
                         int32_t head_dim, float scale, void* stream);
 
+/* ---- memory-bound kernels ------------------------------------------------------------------ */
+
+/* GroupNorm over channels-last bf16 x [B, HW, C] with optional fused SiLU / GELU (act = TAIR_ACT_*).
+ * gamma/beta fp32 [C]; workspace >= tair_groupnorm_workspace_bytes(B, groups) bytes of device memory. */
+int64_t tair_groupnorm_workspace_bytes(int32_t B, int32_t groups);
+int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, const float* beta, int32_t B, int32_t HW,
+                        int32_t C, int32_t groups, float eps, int32_t act, void* workspace, void* stream);
+
+/* Row LayerNorm: y[m,:] = (x[m,:]-mean)/sqrt(var+eps)*gamma+beta; bf16 in/out, fp32 statistics. */
+int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                   int32_t M, int32_t C, float eps, void* stream);
+
+/* One ancestral-sampling update (v-parameterisation), all tensors fp32 [B, per_sample]:
+ *   v      = v_uncond ? v_uncond + cfg_scale*(v_cond - v_uncond) : v_cond
+ *   x0     = sqrt_ac[t]*x - sqrt_1mac[t]*v
+ *   x_prev = coef1[t]*x0 + coef2[t]*x + (t != 0) * sqrt(post_var[t]) * noise
+ * t is the int64 [B] index into the respaced schedule tables (device pointers).  pred_x0 may be NULL. */
+int tair_sampler_update(const float* x, const float* v_cond, const float* v_uncond, float cfg_scale,
+                        const float* noise, float* x_prev, float* pred_x0, const int64_t* t,
+                        const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
+                        const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                        const float* posterior_variance, int32_t B, int32_t per_sample, void* stream);
+
+/* out[b, :] = cos(t*f) || sin(t*f), f_k = exp(-ln(max_period) k/half); t int64 [B]; out bf16 [B, dim]. */
+int tair_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, float max_period, void* stream);
+
+/* (B,C,HW) fp32 -> [B*HW, Cpad] bf16 (zero channel padding) and back ([B*HW, ld] bf16 -> (B,C,HW) fp32). */
+int tair_nchw_to_nhwc_bf16(const float* in, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cpad, void* stream);
+int tair_nhwc_to_nchw_f32(const void* in, int64_t ld, float* out, int32_t B, int32_t C, int32_t HW, void* stream);
+
+/* out[M, C1+C2] = [a | b (+ c)] (c may be NULL); out = a + b over n elements; nearest x2 upsample. All bf16. */
+int tair_concat_add(const void* a, const void* b, const void* c, void* out, int64_t M, int32_t C1, int32_t C2,
+                    void* stream);
+int tair_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+int tair_upsample2x_nhwc(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* Multi-scale deformable attention forward; argument meaning as _C.ms_deform_attn_forward:
+ *   value [B,S,M,D] (fp32, or bf16 when value_bf16), spatial_shapes int64 [L,2] (H,W) and
+ *   level_start_index int64 [L] on the DEVICE, sampling_loc fp32 [B,Lq,M,L,P,2] (x,y in [0,1]),
+ *   attn_weight fp32 [B,Lq,M,L,P]  ->  out [B,Lq,M*D] (fp32, or bf16 when out_bf16).
+ * Unlike the reference there is no im2col_step and no batch-divisibility constraint. */
+int tair_msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const float* sampling_loc, const float* attn_weight, void* out, int32_t B, int32_t S,
+                      int32_t M, int32_t D, int32_t L, int32_t Lq, int32_t P, int32_t value_bf16,
+                      int32_t out_bf16, void* stream);
+
+/* Blend n_tiles fp32 tiles [n_tiles, C, tile, tile] laid out row-major on an n_h x n_w grid with the given
+ * overlap (stride = tile - overlap) into out [C, out_h, out_w] (top-left crop of the canvas). */
+int tair_blend_tiles(const float* tiles, float* out, int32_t n_tiles, int32_t n_h, int32_t n_w, int32_t C,
+                     int32_t tile, int32_t overlap, int32_t out_h, int32_t out_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,18 @@ SIGNATURES = {
     "tair_gemm_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, C.POINTER(Epilogue), _vp]),
     "tair_conv3x3_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(Epilogue), _vp]),
     "tair_attention_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "tair_groupnorm_workspace_bytes": (C.c_int64, [_i32, _i32]),
+    "tair_groupnorm_nhwc": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),
+    "tair_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _f32, _vp]),
+    "tair_sampler_update": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "tair_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
+    "tair_nchw_to_nhwc_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tair_nhwc_to_nchw_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp]),
+    "tair_concat_add": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "tair_add_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "tair_upsample2x_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tair_msda_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tair_blend_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

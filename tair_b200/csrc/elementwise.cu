@@ -1,0 +1,246 @@
+// Memory-bound elementwise / layout kernels of the denoising step.
+//
+//   tair_sampler_update   : v -> x0 -> posterior mean/variance -> x_{t-1}, optional CFG combine
+//                           (terediff/sampler/spaced_sampler.py:141-147,123-131,149-164,167-189)
+//   tair_timestep_embedding: cos||sin sinusoidal embedding (terediff/model/util.py:128-148)
+//   tair_nchw_to_nhwc_bf16 / tair_nhwc_to_nchw_f32 : reference (B,C,H,W) fp32 <-> internal [B*H*W, C] bf16
+//   tair_concat_add       : out = [a | b (+ c)] along channels  (decoder skip: controlnet.py:46-50)
+//   tair_add_bf16         : out = a + b                          (mid-block control add: controlnet.py:41-42)
+//   tair_upsample2x_nhwc  : nearest x2 (unet.py:73-75)
+#include <atomic>
+
+#include "../../include/tair_b200.h"
+#include "common.cuh"
+
+namespace tair {
+extern std::atomic<int64_t> g_launch_count;
+namespace {
+
+__global__ void sampler_update_kernel(const float* __restrict__ x, const float* __restrict__ v_cond,
+                                      const float* __restrict__ v_uncond, const float* __restrict__ noise,
+                                      float* __restrict__ x_prev, float* __restrict__ x0_out,
+                                      const int64_t* __restrict__ t, const float* __restrict__ sqrt_ac,
+                                      const float* __restrict__ sqrt_1mac, const float* __restrict__ coef1,
+                                      const float* __restrict__ coef2, const float* __restrict__ post_var,
+                                      float cfg_scale, int per_sample, int total) {
+  // 4 elements per thread; per_sample % 4 == 0 so a float4 never straddles two samples
+  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= total) return;
+  const int b = i4 / per_sample;
+  const int64_t ti = t[b];
+  const float sa = sqrt_ac[ti], sm = sqrt_1mac[ti], c1 = coef1[ti], c2 = coef2[ti];
+  const float sigma = (ti != 0) ? sqrtf(post_var[ti]) : 0.f;
+  const float4 xv = *reinterpret_cast<const float4*>(x + i4);
+  float4 vv = *reinterpret_cast<const float4*>(v_cond + i4);
+  if (v_uncond != nullptr) {
+    const float4 vu = *reinterpret_cast<const float4*>(v_uncond + i4);
+    vv.x = __fadd_rn(vu.x, __fmul_rn(cfg_scale, __fsub_rn(vv.x, vu.x)));
+    vv.y = __fadd_rn(vu.y, __fmul_rn(cfg_scale, __fsub_rn(vv.y, vu.y)));
+    vv.z = __fadd_rn(vu.z, __fmul_rn(cfg_scale, __fsub_rn(vv.z, vu.z)));
+    vv.w = __fadd_rn(vu.w, __fmul_rn(cfg_scale, __fsub_rn(vv.w, vu.w)));
+  }
+  const float4 nz = *reinterpret_cast<const float4*>(noise + i4);
+  float4 x0, out;
+  // same operation order as the reference, no fused multiply-add, so fp32 results are bit-identical
+  x0.x = __fsub_rn(__fmul_rn(sa, xv.x), __fmul_rn(sm, vv.x));
+  x0.y = __fsub_rn(__fmul_rn(sa, xv.y), __fmul_rn(sm, vv.y));
+  x0.z = __fsub_rn(__fmul_rn(sa, xv.z), __fmul_rn(sm, vv.z));
+  x0.w = __fsub_rn(__fmul_rn(sa, xv.w), __fmul_rn(sm, vv.w));
+  out.x = __fadd_rn(__fadd_rn(__fmul_rn(c1, x0.x), __fmul_rn(c2, xv.x)), __fmul_rn(sigma, nz.x));
+  out.y = __fadd_rn(__fadd_rn(__fmul_rn(c1, x0.y), __fmul_rn(c2, xv.y)), __fmul_rn(sigma, nz.y));
+  out.z = __fadd_rn(__fadd_rn(__fmul_rn(c1, x0.z), __fmul_rn(c2, xv.z)), __fmul_rn(sigma, nz.z));
+  out.w = __fadd_rn(__fadd_rn(__fmul_rn(c1, x0.w), __fmul_rn(c2, xv.w)), __fmul_rn(sigma, nz.w));
+  *reinterpret_cast<float4*>(x_prev + i4) = out;
+  if (x0_out != nullptr) *reinterpret_cast<float4*>(x0_out + i4) = x0;
+}
+
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B,
+                                          int dim, float max_period) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * dim) return;
+  const int b = i / dim, j = i - b * dim;
+  float val = 0.f;
+  if (j < 2 * half) {
+    const int k = j < half ? j : j - half;
+    const float freq = expf(-logf(max_period) * (float)k / (float)half);
+    const float ang = (float)t[b] * freq;
+    val = j < half ? cosf(ang) : sinf(ang);
+  }
+  out[i] = __float2bfloat16(val);
+}
+
+// (B, C, HW) fp32 -> [B, HW, Cpad] bf16 (channels >= C zero-filled); 32x32 smem transpose
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int HW,
+                                    int Cpad) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, px = p0 + tx;
+    tile[k][tx] = (c < C && px < HW) ? in[((int64_t)b * C + c) * HW + px] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int px = p0 + k, c = c0 + tx;
+    if (px < HW && c < Cpad) out[((int64_t)b * HW + px) * Cpad + c] = __float2bfloat16(tile[tx][k]);
+  }
+}
+
+// [B, HW, ld] bf16 (first C channels) -> (B, C, HW) fp32
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int HW,
+                                    int64_t ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int k = ty; k < 32; k += 8) {
+    const int px = p0 + k, c = c0 + tx;
+    tile[k][tx] = (px < HW && c < C) ? __bfloat162float(in[((int64_t)b * HW + px) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, px = p0 + tx;
+    if (c < C && px < HW) out[((int64_t)b * C + c) * HW + px] = tile[tx][k];
+  }
+}
+
+__device__ __forceinline__ uint4 add_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  float2 x, y;
+  x = unpack_bf16(a.x); y = unpack_bf16(b.x); r.x = pack_bf16(x.x + y.x, x.y + y.y);
+  x = unpack_bf16(a.y); y = unpack_bf16(b.y); r.y = pack_bf16(x.x + y.x, x.y + y.y);
+  x = unpack_bf16(a.z); y = unpack_bf16(b.z); r.z = pack_bf16(x.x + y.x, x.y + y.y);
+  x = unpack_bf16(a.w); y = unpack_bf16(b.w); r.w = pack_bf16(x.x + y.x, x.y + y.y);
+  return r;
+}
+
+// out[M, C1+C2] = [a[M,C1] | b[M,C2] (+ c[M,C2])]; one 16-byte vector per thread
+__global__ void concat_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                  const uint4* __restrict__ c, uint4* __restrict__ out, int64_t M, int v1, int v2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vt = v1 + v2;
+  if (i >= M * vt) return;
+  const int64_t row = i / vt;
+  const int col = (int)(i - row * vt);
+  uint4 r;
+  if (col < v1) {
+    r = __ldg(a + row * v1 + col);
+  } else {
+    const int64_t j = row * v2 + (col - v1);
+    r = __ldg(b + j);
+    if (c != nullptr) r = add_bf16x8(r, __ldg(c + j));
+  }
+  out[i] = r;
+}
+
+__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                           int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = add_bf16x8(__ldg(a + i), __ldg(b + i));
+}
+
+// [B, H, W, C] -> [B, 2H, 2W, C] nearest; one 16-byte vector of the OUTPUT per thread
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * 4 * H * W * vc;
+  if (i >= total) return;
+  const int v = (int)(i % vc);
+  int64_t r = i / vc;
+  const int xo = (int)(r % (2 * W)); r /= 2 * W;
+  const int yo = (int)(r % (2 * H));
+  const int b = (int)(r / (2 * H));
+  out[i] = __ldg(in + (((int64_t)b * H + (yo >> 1)) * W + (xo >> 1)) * vc + v);
+}
+
+}  // namespace
+}  // namespace tair
+
+using namespace tair;
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
+
+extern "C" int tair_sampler_update(const float* x, const float* v_cond, const float* v_uncond, float cfg_scale,
+                                   const float* noise, float* x_prev, float* pred_x0, const int64_t* t,
+                                   const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
+                                   const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                                   const float* posterior_variance, int32_t B, int32_t per_sample, void* stream) {
+  TAIR_REQUIRE(x && v_cond && noise && x_prev && t, "sampler_update: NULL pointer");
+  TAIR_REQUIRE(sqrt_alphas_cumprod && sqrt_one_minus_alphas_cumprod && posterior_mean_coef1 &&
+                   posterior_mean_coef2 && posterior_variance, "sampler_update: NULL schedule table");
+  TAIR_REQUIRE(B > 0 && per_sample > 0 && per_sample % 4 == 0, "sampler_update: per_sample must be a multiple of 4");
+  TAIR_REQUIRE(al16(x) && al16(v_cond) && al16(noise) && al16(x_prev) && (!v_uncond || al16(v_uncond)) &&
+                   (!pred_x0 || al16(pred_x0)), "sampler_update: tensors must be 16-byte aligned");
+  const int total = B * per_sample;
+  const int threads = 256, grid = (total / 4 + threads - 1) / threads;
+  sampler_update_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, v_cond, v_uncond, noise, x_prev, pred_x0, t, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod,
+      posterior_mean_coef1, posterior_mean_coef2, posterior_variance, cfg_scale, per_sample, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("sampler_update_kernel");
+}
+
+extern "C" int tair_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, float max_period,
+                                       void* stream) {
+  TAIR_REQUIRE(t && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
+  const int n = B * dim;
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, reinterpret_cast<__nv_bfloat16*>(out), B, dim, max_period);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("timestep_embedding_kernel");
+}
+
+extern "C" int tair_nchw_to_nhwc_bf16(const float* in, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cpad,
+                                      void* stream) {
+  TAIR_REQUIRE(in && out && B > 0 && C > 0 && HW > 0 && Cpad >= C, "nchw_to_nhwc: bad arguments");
+  dim3 grid((HW + 31) / 32, (Cpad + 31) / 32, B), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), C, HW, Cpad);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int tair_nhwc_to_nchw_f32(const void* in, int64_t ld, float* out, int32_t B, int32_t C, int32_t HW,
+                                     void* stream) {
+  TAIR_REQUIRE(in && out && B > 0 && C > 0 && HW > 0 && ld >= C, "nhwc_to_nchw: bad arguments");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), out, C, HW, ld);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int tair_concat_add(const void* a, const void* b, const void* c, void* out, int64_t M, int32_t C1,
+                               int32_t C2, void* stream) {
+  TAIR_REQUIRE(a && b && out && M > 0 && C1 > 0 && C2 > 0, "concat_add: bad arguments");
+  TAIR_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "concat_add: channel counts must be multiples of 8");
+  TAIR_REQUIRE(al16(a) && al16(b) && al16(out) && (!c || al16(c)), "concat_add: tensors must be 16-byte aligned");
+  const int64_t n = M * ((C1 + C2) / 8);
+  concat_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<const uint4*>(c),
+      reinterpret_cast<uint4*>(out), M, C1 / 8, C2 / 8);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("concat_add_kernel");
+}
+
+extern "C" int tair_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  TAIR_REQUIRE(a && b && out && n > 0 && n % 8 == 0, "add: n must be a positive multiple of 8");
+  TAIR_REQUIRE(al16(a) && al16(b) && al16(out), "add: tensors must be 16-byte aligned");
+  const int64_t nv = n / 8;
+  add_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), nv);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("add_kernel");
+}
+
+extern "C" int tair_upsample2x_nhwc(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                                    void* stream) {
+  TAIR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x: bad arguments");
+  TAIR_REQUIRE(al16(in) && al16(out), "upsample2x: tensors must be 16-byte aligned");
+  const int64_t n = (int64_t)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("upsample2x_kernel");
+}

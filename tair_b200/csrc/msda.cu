@@ -1,0 +1,144 @@
+// Multi-scale deformable attention forward (bilinear gather + weighted sum) for sm_100a.
+//
+// Drop-in for `_C.ms_deform_attn_forward` (testr/adet/layers/csrc/vision.cpp:52-55 ->
+// ms_deform_attn_cuda.cu:20-80 -> ms_deformable_im2col_gpu_kernel, ms_deform_im2col_cuda.cuh:237-299,
+// bilinear tap rule :33-84).  Semantics kept exactly:
+//   w_im = loc_x * W_l - 0.5, h_im = loc_y * H_l - 0.5; a sample contributes only if
+//   h_im > -1 && w_im > -1 && h_im < H_l && w_im < W_l; each of the 4 taps is individually
+//   bounds-checked and reads zero outside; value is addressed as ((b*S + start_l + y*W_l + x)*M + m)*D + c.
+//
+// Mapping (warp-cooperative): one work item = (b, q, head); D/8 lanes share an item, each lane owning 8
+// consecutive channels, so every tap is a single 16-byte (bf16) / 32-byte (fp32) load per lane, the lanes
+// of a head read one contiguous D-channel segment, and a warp writes 32*8 consecutive output channels.
+// The reference kernel uses one thread per output scalar, re-reading every location/weight/shape scalar
+// D times and doing the index arithmetic in int64 per tap.
+#include <atomic>
+
+#include "../../include/tair_b200.h"
+#include "common.cuh"
+
+namespace tair {
+extern std::atomic<int64_t> g_launch_count;
+namespace {
+
+struct MsdaParams {
+  const void* value;
+  const int64_t* shapes;  // [L,2] (H,W), device
+  const int64_t* starts;  // [L], device
+  const float* loc;       // [B,Lq,M,L,P,2]
+  const float* attw;      // [B,Lq,M,L,P]
+  void* out;              // [B,Lq,M*D]
+  int B, S, M, D, L, Lq, P;
+  int lanes_per_item;     // D / 8
+  long items;             // B*Lq*M
+};
+
+template <typename VT>
+__device__ __forceinline__ void load_vec8(const VT* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_vec8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load_vec8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+template <typename VT, typename OT>
+__global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaParams p) {
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long item = gtid / p.lanes_per_item;
+  const int part = (int)(gtid - item * p.lanes_per_item);
+  if (item >= p.items) return;
+  const int m = (int)(item % p.M);
+  const long bq = item / p.M;
+  const int b = (int)(bq / p.Lq);
+  const VT* vbase = reinterpret_cast<const VT*>(p.value) + ((long)b * p.S * p.M + m) * p.D + part * 8;
+  const long row_stride = (long)p.M * p.D;
+  const float* locp = p.loc + item * p.L * p.P * 2;
+  const float* wp = p.attw + item * p.L * p.P;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int l = 0; l < p.L; ++l) {
+    const int H = (int)__ldg(p.shapes + 2 * l), W = (int)__ldg(p.shapes + 2 * l + 1);
+    const VT* vl = vbase + (long)__ldg(p.starts + l) * row_stride;
+    for (int s = 0; s < p.P; ++s) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(locp) + l * p.P + s);
+      const float aw = __ldg(wp + l * p.P + s);
+      const float h_im = xy.y * (float)H - 0.5f;
+      const float w_im = xy.x * (float)W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+        const int h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        float v1[8], v2[8], v3[8], v4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v1[i] = 0.f; v2[i] = 0.f; v3[i] = 0.f; v4[i] = 0.f; }
+        const bool top = h_low >= 0, bot = h_high <= H - 1, left = w_low >= 0, right = w_high <= W - 1;
+        if (top && left) load_vec8<VT>(vl + ((long)h_low * W + w_low) * row_stride, v1);
+        if (top && right) load_vec8<VT>(vl + ((long)h_low * W + w_high) * row_stride, v2);
+        if (bot && left) load_vec8<VT>(vl + ((long)h_high * W + w_low) * row_stride, v3);
+        if (bot && right) load_vec8<VT>(vl + ((long)h_high * W + w_high) * row_stride, v4);
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float val = w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
+          acc[i] += val * aw;
+        }
+      }
+    }
+  }
+  OT* op = reinterpret_cast<OT*>(p.out) + item * p.D + part * 8;
+  if constexpr (sizeof(OT) == 4) {
+    reinterpret_cast<float4*>(op)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(op)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
+    uint4 q;
+    q.x = pack_bf16(acc[0], acc[1]); q.y = pack_bf16(acc[2], acc[3]);
+    q.z = pack_bf16(acc[4], acc[5]); q.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(op) = q;
+  }
+}
+
+}  // namespace
+}  // namespace tair
+
+using namespace tair;
+
+extern "C" int tair_msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                 const float* sampling_loc, const float* attn_weight, void* out, int32_t B,
+                                 int32_t S, int32_t M, int32_t D, int32_t L, int32_t Lq, int32_t P,
+                                 int32_t value_bf16, int32_t out_bf16, void* stream) {
+  TAIR_REQUIRE(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
+               "msda_forward: NULL pointer");
+  TAIR_REQUIRE(B > 0 && S > 0 && M > 0 && D > 0 && L > 0 && Lq > 0 && P > 0, "msda_forward: bad shape");
+  TAIR_REQUIRE(D % 8 == 0 && D <= 256 && (32 % (D / 8)) == 0,
+               "msda_forward: channels per head must be 8,16,32,64,128 or 256 (got %d)", D);
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(value) % 32) == 0 && (reinterpret_cast<uintptr_t>(out) % 32) == 0 &&
+                   (reinterpret_cast<uintptr_t>(sampling_loc) % 8) == 0,
+               "msda_forward: tensors must be 32-byte aligned");
+  MsdaParams p{};
+  p.value = value; p.shapes = spatial_shapes; p.starts = level_start_index;
+  p.loc = sampling_loc; p.attw = attn_weight; p.out = out;
+  p.B = B; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P;
+  p.lanes_per_item = D / 8;
+  p.items = (long)B * Lq * M;
+  const long threads_total = p.items * p.lanes_per_item;
+  const int block = 256;
+  const long grid = (threads_total + block - 1) / block;
+  TAIR_REQUIRE(grid < (1l << 31), "msda_forward: problem too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (value_bf16 && out_bf16) msda_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)grid, block, 0, st>>>(p);
+  else if (value_bf16) msda_fwd_kernel<__nv_bfloat16, float><<<(unsigned)grid, block, 0, st>>>(p);
+  else if (out_bf16) msda_fwd_kernel<float, __nv_bfloat16><<<(unsigned)grid, block, 0, st>>>(p);
+  else msda_fwd_kernel<float, float><<<(unsigned)grid, block, 0, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("msda_fwd_kernel");
+}

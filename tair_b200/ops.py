@@ -144,3 +144,177 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, H: i
                                         B, H, Lq, Lk, head_dim, float(scale), _stream())
     _lib.check(rc, "tair_attention_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# memory-bound kernels
+# ---------------------------------------------------------------------------------------------
+_gn_ws: dict = {}
+
+
+def _gn_workspace(device, B: int, groups: int) -> torch.Tensor:
+    need = int(_lib.lib().tair_groupnorm_workspace_bytes(B, groups))
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), device=device, dtype=torch.uint8)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, groups: int = 32, eps: float = 1e-5,
+              act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU/GELU) on channels-last bf16 x [B, ..., C] (any number of spatial dims)."""
+    _cuda(x, "x", BF16), _cuda(gamma, "gamma", torch.float32), _cuda(beta, "beta", torch.float32)
+    if not x.is_contiguous():
+        raise TairError("groupnorm: x must be contiguous channels-last")
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    if out is None:
+        out = torch.empty_like(x)
+    ws = _gn_workspace(x.device, B, groups)
+    rc = _lib.lib().tair_groupnorm_nhwc(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, HW, C,
+                                        groups, float(eps), act, ws.data_ptr(), _stream())
+    _lib.check(rc, "tair_groupnorm_nhwc")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, "x", BF16), _cuda(gamma, "gamma", torch.float32), _cuda(beta, "beta", torch.float32)
+    x2, ldx = _rows(x, "x")
+    if out is None:
+        out = torch.empty((x2.shape[0], x2.shape[1]), device=x.device, dtype=BF16)
+    o2, ldy = _rows(out, "out")
+    rc = _lib.lib().tair_layernorm(x2.data_ptr(), ldx, o2.data_ptr(), ldy, gamma.data_ptr(), beta.data_ptr(),
+                                   x2.shape[0], x2.shape[1], float(eps), _stream())
+    _lib.check(rc, "tair_layernorm")
+    return out
+
+
+def sampler_update(x, v_cond, noise, t, tables, *, v_uncond=None, cfg_scale: float = 1.0, out=None, pred_x0=None):
+    """tables = (sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
+    posterior_variance): fp32 CUDA vectors; t int64 [B]."""
+    for tt, n in ((x, "x"), (v_cond, "v"), (noise, "noise")):
+        _cuda(tt, n, torch.float32)
+        if not tt.is_contiguous():
+            raise TairError(f"sampler_update: {n} must be contiguous")
+    _cuda(t, "t", torch.int64)
+    B = x.shape[0]
+    per = x.numel() // B
+    if out is None:
+        out = torch.empty_like(x)
+    tabs = [_cuda(tb, "schedule table", torch.float32).data_ptr() for tb in tables]
+    rc = _lib.lib().tair_sampler_update(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond), float(cfg_scale),
+                                        noise.data_ptr(), out.data_ptr(), _ptr(pred_x0), t.data_ptr(), *tabs, B, per,
+                                        _stream())
+    _lib.check(rc, "tair_sampler_update")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    _cuda(t, "t", torch.int64)
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=BF16)
+    rc = _lib.lib().tair_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, float(max_period), _stream())
+    _lib.check(rc, "tair_timestep_embedding")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    """(B,C,H,W) fp32 -> [B,H,W,Cpad] bf16 with zero channel padding."""
+    _cuda(x, "x", torch.float32)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    cp = c_pad or C
+    out = torch.empty((B, H, W, cp), device=x.device, dtype=BF16)
+    rc = _lib.lib().tair_nchw_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, H * W, cp, _stream())
+    _lib.check(rc, "tair_nchw_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    """[B,H,W,C'] bf16 -> (B,C,H,W) fp32 keeping the first ``channels`` channels."""
+    _cuda(x, "x", BF16)
+    B, H, W, ld = x.shape
+    if not x.is_contiguous():
+        raise TairError("nhwc_to_nchw: x must be contiguous")
+    C = channels or ld
+    out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().tair_nhwc_to_nchw_f32(x.data_ptr(), ld, out.data_ptr(), B, C, H * W, _stream())
+    _lib.check(rc, "tair_nhwc_to_nchw_f32")
+    return out
+
+
+def concat_add(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """channels-last concat [a | b (+c)] for tensors [..., C1], [..., C2]."""
+    _cuda(a, "a", BF16), _cuda(b, "b", BF16)
+    if not (a.is_contiguous() and b.is_contiguous() and (c is None or c.is_contiguous())):
+        raise TairError("concat_add: inputs must be contiguous")
+    C1, C2 = a.shape[-1], b.shape[-1]
+    M = a.numel() // C1
+    out = torch.empty((*a.shape[:-1], C1 + C2), device=a.device, dtype=BF16)
+    rc = _lib.lib().tair_concat_add(a.data_ptr(), b.data_ptr(), _ptr(c), out.data_ptr(), M, C1, C2, _stream())
+    _lib.check(rc, "tair_concat_add")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(a, "a", BF16), _cuda(b, "b", BF16)
+    if not (a.is_contiguous() and b.is_contiguous()) or a.shape != b.shape:
+        raise TairError("add: inputs must be contiguous and of equal shape")
+    if out is None:
+        out = torch.empty_like(a)
+    rc = _lib.lib().tair_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream())
+    _lib.check(rc, "tair_add_bf16")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x, "x", BF16)
+    if x.dim() != 4 or not x.is_contiguous():
+        raise TairError("upsample2x: x must be contiguous [B,H,W,C]")
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=BF16)
+    rc = _lib.lib().tair_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _stream())
+    _lib.check(rc, "tair_upsample2x_nhwc")
+    return out
+
+
+def msda_forward(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                 sampling_locations: torch.Tensor, attention_weights: torch.Tensor,
+                 out_dtype=None) -> torch.Tensor:
+    """Same arguments as ``_C.ms_deform_attn_forward`` minus im2col_step (vision.cpp:52-55).
+    value [B,S,M,D] fp32|bf16; shapes int64 [L,2]; start int64 [L]; loc fp32 [B,Lq,M,L,P,2]; w fp32 [B,Lq,M,L,P]."""
+    _cuda(value, "value")
+    if value.dtype not in (torch.float32, BF16):
+        raise TairError("msda_forward: value must be fp32 or bf16")
+    _cuda(spatial_shapes, "spatial_shapes", torch.int64), _cuda(level_start_index, "level_start_index", torch.int64)
+    _cuda(sampling_locations, "sampling_locations", torch.float32)
+    _cuda(attention_weights, "attention_weights", torch.float32)
+    for tt, n in ((value, "value"), (sampling_locations, "sampling_locations"), (attention_weights, "attention_weights"),
+                  (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index")):
+        if not tt.is_contiguous():
+            raise TairError(f"msda_forward: {n} must be contiguous")
+    B, S, M, D = value.shape
+    _, Lq, M2, L, P, two = sampling_locations.shape
+    if M2 != M or two != 2 or tuple(attention_weights.shape) != (B, Lq, M, L, P):
+        raise TairError("msda_forward: inconsistent shapes")
+    out_dtype = out_dtype or value.dtype
+    out = torch.empty((B, Lq, M * D), device=value.device, dtype=out_dtype)
+    rc = _lib.lib().tair_msda_forward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                      sampling_locations.data_ptr(), attention_weights.data_ptr(), out.data_ptr(),
+                                      B, S, M, D, L, Lq, P, int(value.dtype == BF16), int(out_dtype == BF16), _stream())
+    _lib.check(rc, "tair_msda_forward")
+    return out
+
+
+def blend_tiles(tiles: torch.Tensor, n_h: int, n_w: int, overlap: int, out_h: int, out_w: int) -> torch.Tensor:
+    """tiles [P, C, T, T] fp32 in row-major grid order -> (1, C, out_h, out_w) fp32."""
+    _cuda(tiles, "tiles", torch.float32)
+    if tiles.dim() != 4 or tiles.shape[2] != tiles.shape[3] or not tiles.is_contiguous():
+        raise TairError("blend_tiles: tiles must be contiguous [P,C,T,T]")
+    P_, Cc, T, _ = tiles.shape
+    out = torch.empty((1, Cc, out_h, out_w), device=tiles.device, dtype=torch.float32)
+    rc = _lib.lib().tair_blend_tiles(tiles.data_ptr(), out.data_ptr(), P_, n_h, n_w, Cc, T, overlap, out_h, out_w, _stream())
+    _lib.check(rc, "tair_blend_tiles")
+    return out
