@@ -138,7 +138,8 @@ def install() -> None:
         _stub("omegaconf.listconfig", ListConfig=ListConfig)
     for name in ("accelerate", "accelerate.utils", "pyiqa", "wandb"):
         if not _try(name):
-            _stub(name, Accelerator=object, set_seed=lambda *_a, **_k: None, create_metric=lambda *_a, **_k: None)
+            _stub(name, Accelerator=object, DistributedDataParallelKwargs=object, set_seed=lambda *_a, **_k: None,
+                  create_metric=lambda *_a, **_k: None)
     if not _try("detectron2"):
         _stub("detectron2")
         _stub("detectron2.structures", Instances=_Instances, ImageList=object, Boxes=object)

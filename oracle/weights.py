@@ -54,3 +54,9 @@ def seeded_state_dict(manifest: Mapping[str, Sequence[int]], seed: int = 1234) -
 
 def manifest_of(module: torch.nn.Module) -> Dict[str, list]:
     return {k: list(v.shape) for k, v in module.state_dict().items() if v.dtype.is_floating_point}
+
+
+def seeded_randn(shape, seed: int, scale: float = 1.0) -> torch.Tensor:
+    """Deterministic CPU N(0, scale^2) tensor; the input generator shared by make_golden.py and the tests."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(tuple(shape), generator=g) * scale

@@ -52,12 +52,13 @@ __global__ void gn_stats_kernel(const GnParams p) {
   const int vec = threadIdx.x % p.vec_per_row;
   const int rsub = threadIdx.x / p.vec_per_row;
   const int c0 = vec * 8;
-  const int g0 = c0 / p.cpg;
-  int nsplit = (g0 + 1) * p.cpg - c0;  // channels [c0, c0+nsplit) belong to g0, the rest to g0+1
-  if (nsplit > 8) nsplit = 8;
   for (int i = threadIdx.x; i < p.G; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
   __syncthreads();
-  float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+  // per-channel partial sums (the thread's 8 channels are fixed across rows), folded per group at the end;
+  // works for any channels-per-group, including groups narrower than one 8-channel vector
+  float sm[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
   const int r0 = slab * p.rows_per_slab;
   int r1 = r0 + p.rows_per_slab;
   if (r1 > p.HW) r1 = p.HW;
@@ -66,16 +67,23 @@ __global__ void gn_stats_kernel(const GnParams p) {
     float f[8];
     load8(xb + (int64_t)r * p.C, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < nsplit) { sa += f[i]; qa += f[i] * f[i]; }
-      else { sb += f[i]; qb += f[i] * f[i]; }
-    }
+    for (int i = 0; i < 8; ++i) { sm[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
   }
-  atomicAdd(&s_sum[g0], sa);
-  atomicAdd(&s_sq[g0], qa);
-  if (nsplit < 8) {
-    atomicAdd(&s_sum[g0 + 1], sb);
-    atomicAdd(&s_sq[g0 + 1], qb);
+  {
+    int g = c0 / p.cpg;
+    float ps = 0.f, pq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gi = (c0 + i) / p.cpg;
+      if (gi != g) {
+        atomicAdd(&s_sum[g], ps);
+        atomicAdd(&s_sq[g], pq);
+        g = gi; ps = 0.f; pq = 0.f;
+      }
+      ps += sm[i]; pq += sq[i];
+    }
+    atomicAdd(&s_sum[g], ps);
+    atomicAdd(&s_sq[g], pq);
   }
   __syncthreads();
   float* w = p.ws + ((int64_t)(b * p.slabs + slab) * p.G) * 2;
@@ -205,7 +213,6 @@ extern "C" int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, c
   TAIR_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 64, "groupnorm: bad shape");
   TAIR_REQUIRE(C % groups == 0 && C % 8 == 0, "groupnorm: C must divide by groups and by 8 (C=%d)", C);
   const int cpg = C / groups;
-  TAIR_REQUIRE(cpg >= 8, "groupnorm: channels per group must be >= 8 (got %d)", cpg);
   TAIR_REQUIRE(act == TAIR_ACT_NONE || act == TAIR_ACT_SILU || act == TAIR_ACT_GELU,
                "groupnorm: activation must be none, SiLU or GELU");
   TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(y) % 16) == 0,

@@ -1,0 +1,78 @@
+"""ControlLDM — the restoration model wrapper (terediff/model/cldm.py:20-217) on the sm_100a kernels.
+
+``forward(x_noisy, t, cond) -> (eps, extracted_feats[4])`` keeps the reference contract (cldm.py:160-179):
+IRControlNet on (x_noisy || c_img) -> per-block ``control_scales`` -> controlled UNet.  Both networks exchange
+channels-last bf16 tensors directly; only the public inputs/outputs are (B,C,H,W) fp32.
+
+The VAE and the OpenCLIP text encoder are not on the per-step hot path (SURVEY.md §8f "next"); they can be attached
+as ordinary torch modules (``attach_vae`` / ``attach_clip``) so ``prepare_condition`` / ``vae_decode`` keep working.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+from .controlnet import ControlledUnetModel, ControlNet
+from .util import BF16
+
+
+class ControlLDM(nn.Module):
+    def __init__(self, unet_cfg: dict, controlnet_cfg: dict, latent_scale_factor: float = 0.18215, vae_cfg=None,
+                 clip_cfg=None):
+        super().__init__()
+        self.unet = ControlledUnetModel(**unet_cfg)
+        self.controlnet = ControlNet(**controlnet_cfg)
+        self.scale_factor = latent_scale_factor
+        self.control_scales = [1.0] * 13  # cldm.py:30
+        self.vae: Optional[nn.Module] = None
+        self.clip: Optional[nn.Module] = None
+        self.return_nhwc_feats = False  # True: hand channels-last bf16 features to the TESTR head (no round trip)
+
+    # -- optional non-hot-path submodules ---------------------------------------------------------
+    def attach_vae(self, vae: nn.Module) -> None:
+        self.vae = vae
+
+    def attach_clip(self, clip: nn.Module) -> None:
+        self.clip = clip
+
+    @torch.no_grad()
+    def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
+        """cldm.py:121-141 (untiled)."""
+        if self.vae is None:
+            raise RuntimeError("ControlLDM.vae_decode: no VAE attached")
+        return self.vae.decode(z / self.scale_factor)
+
+    @torch.no_grad()
+    def vae_encode(self, image: torch.Tensor, sample: bool = True) -> torch.Tensor:
+        """cldm.py:92-119 (untiled)."""
+        if self.vae is None:
+            raise RuntimeError("ControlLDM.vae_encode: no VAE attached")
+        post = self.vae.encode(image)
+        return (post.sample() if sample else post.mode()) * self.scale_factor
+
+    @torch.no_grad()
+    def prepare_condition(self, cond_img: torch.Tensor, txt: List[str]) -> Dict[str, torch.Tensor]:
+        """cldm.py:143-158."""
+        if self.clip is None:
+            raise RuntimeError("ControlLDM.prepare_condition: no text encoder attached")
+        return dict(c_txt=self.clip.encode(txt), c_img=self.vae_encode(cond_img * 2 - 1, sample=False))
+
+    # -- the hot path -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x_noisy: torch.Tensor, t: torch.Tensor, cond: Dict[str, torch.Tensor]):
+        c_txt = cond["c_txt"]
+        unet, cn = self.unet, self.controlnet
+        control = None
+        if "c_img" in cond:
+            xh = torch.cat((x_noisy, cond["c_img"]), dim=1)
+            control = cn.forward_nhwc(cn._embed_input(xh), t, c_txt)
+            if any(s != 1.0 for s in self.control_scales):
+                control = [(c.float() * s).to(BF16) for c, s in zip(control, self.control_scales)]
+        out, feats = unet.forward_nhwc(unet._embed_input(x_noisy), t, c_txt, control, False)
+        eps = ops.nhwc_to_nchw(out, unet.out_channels)
+        if not self.return_nhwc_feats:
+            feats = [ops.nhwc_to_nchw(f) for f in feats]
+        return eps, feats

@@ -1,0 +1,141 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (imported from /root/reference
+through oracle/ref_harness.py).  Run here (build container) only:
+
+    python tests/golden/make_golden.py [unet] [sched] [msda] [merge] [testr] [manifest]
+
+The reference has no tests or known-answer vectors of its own for this path, so these fixtures —
+outputs of the reference's own modules on seeded inputs/weights — are what pins the oracle; the GPU box, which has
+no reference tree, checks the oracle (and through it the CUDA path) against them.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_harness as H  # noqa: E402
+from oracle import weights as Wt  # noqa: E402
+
+NARROW = dict(model_channels=64, context_dim=128)
+
+
+def seeded(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+def gen_manifest():
+    out = {}
+    for name, kw in (("narrow", NARROW), ("full", {})):
+        out[f"unet_{name}"] = Wt.manifest_of(H.build_unet(**kw))
+        out[f"controlnet_{name}"] = Wt.manifest_of(H.build_controlnet(**kw))
+    ts = H.build_testr()
+    out["testr"] = Wt.manifest_of(ts)
+    with open(os.path.join(HERE, "manifests.json"), "w") as f:
+        json.dump(out, f)
+    print("manifests:", {k: len(v) for k, v in out.items()})
+
+
+def gen_unet():
+    u, c = H.build_unet(**NARROW), H.build_controlnet(**NARROW)
+    u.load_state_dict(Wt.seeded_state_dict(Wt.manifest_of(u)))
+    c.load_state_dict(Wt.seeded_state_dict(Wt.manifest_of(c)))
+    B = 2
+    x, hint = seeded((B, 4, 32, 32), 1), seeded((B, 4, 32, 32), 2)
+    ctx = seeded((B, 77, 128), 3)
+    t = torch.tensor([999, 500])
+    with torch.no_grad():
+        ctrl = c(x=x, hint=hint, timesteps=t, context=ctx)
+        out, feats = u(x=x, timesteps=t, context=ctx, control=[k.clone() for k in ctrl], only_mid_control=False)
+    np.savez_compressed(os.path.join(HERE, "unet_narrow.npz"), t=t.numpy(), out=out.numpy(),
+                        ctrl0=ctrl[0][:, ::4, ::2, ::2].numpy(), ctrl12=ctrl[12].numpy()[:, ::4],
+                        **{f"feat{i}": f[:, ::4, ::2, ::2].numpy() for i, f in enumerate(feats)})
+    print("unet_narrow: out std", out.std().item())
+
+
+def gen_sched():
+    H.install()
+    from terediff.model.gaussian_diffusion import enforce_zero_terminal_snr, make_beta_schedule
+    from terediff.sampler.spaced_sampler import SpacedSampler
+    betas = enforce_zero_terminal_snr(make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.0120))
+    s = SpacedSampler(betas, "v", False)
+    s.make_schedule(50)
+    names = ["sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+             "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+             "posterior_mean_coef1", "posterior_mean_coef2"]
+    d = {n: getattr(s, n).numpy() for n in names}
+    d["timesteps"] = s.timesteps
+    # one p_sample through the reference with a stub model and injected noise
+    x, v, noise = seeded((2, 4, 8, 8), 11), seeded((2, 4, 8, 8), 12), seeded((2, 4, 8, 8), 13)
+    orig = torch.randn_like
+    for idx in (49, 7, 0):
+        t = torch.full((2,), idx, dtype=torch.long)
+        torch.randn_like = lambda _x: noise
+        try:
+            xp, _ = s.p_sample(lambda _x, _t, _c: (v, None), x, t, t, {}, None, 1.0)
+        finally:
+            torch.randn_like = orig
+        d[f"x_prev_t{idx}"] = xp.numpy()
+    np.savez_compressed(os.path.join(HERE, "schedule_50.npz"), **d)
+    print("schedule_50: timesteps", s.timesteps[:4], "...", s.timesteps[-3:])
+
+
+def gen_msda():
+    H.install()
+    from testr.adet.layers.ms_deform_attn import ms_deform_attn_core_pytorch
+    shapes = [(8, 8), (4, 6), (3, 3)]
+    S = sum(h * w for h, w in shapes)
+    B, M, D, Lq, L, P = 2, 8, 32, 24, 3, 4
+    value = seeded((B, S, M, D), 21)
+    loc = torch.rand((B, Lq, M, L, P, 2), generator=torch.Generator().manual_seed(22)) * 1.4 - 0.2
+    w = torch.softmax(seeded((B, Lq, M, L * P), 23), -1).view(B, Lq, M, L, P)
+    out = ms_deform_attn_core_pytorch(value, shapes, loc, w)
+    np.savez_compressed(os.path.join(HERE, "msda_case.npz"), shapes=np.array(shapes), out=out.numpy())
+    print("msda_case: out std", out.std().item())
+
+
+def gen_merge():
+    H.install()
+    import val_patches as vp
+    d = {}
+    for name, (oh, ow) in (("a", (200, 300)), ("b", (128, 128)), ("c", (130, 250))):
+        n = len(vp.split_image_with_overlap(__import__("PIL.Image", fromlist=["Image"]).fromarray(
+            np.zeros((oh, ow, 3), np.uint8)), 128, 16))
+        g = torch.Generator().manual_seed(31)
+        tl = [torch.rand((1, 3, 512, 512), generator=g) for _ in range(n)]
+        m = vp.merge_patches_with_overlap(tl, (oh, ow), 512, 64)
+        d[f"{name}_size"] = np.array([oh, ow, n])
+        d[f"{name}_sum"] = np.array(m.double().sum().item())
+        d[f"{name}_sample"] = m[0, :, ::37, ::41].numpy()
+    np.savez_compressed(os.path.join(HERE, "merge_case.npz"), **d)
+    print("merge_case:", {k: v.tolist() for k, v in d.items() if k.endswith("size")})
+
+
+def gen_testr():
+    ts = H.build_testr()
+    ts.load_state_dict(Wt.seeded_state_dict(Wt.manifest_of(ts)), strict=False)
+    B = 1
+    feats = [seeded((B, 1280, 16, 16), 41), seeded((B, 1280, 32, 32), 42), seeded((B, 640, 64, 64), 43),
+             seeded((B, 320, 64, 64), 44)]
+    with torch.no_grad():
+        out = ts.testr(feats)
+        _, res = ts(feats, None, "VAL")
+    r = res[0]
+    np.savez_compressed(os.path.join(HERE, "testr_full.npz"), pred_logits=out["pred_logits"].numpy(),
+                        pred_ctrl_points=out["pred_ctrl_points"].numpy(), pred_texts=out["pred_texts"].numpy(),
+                        enc_logits=out["enc_outputs"]["pred_logits"].numpy()[:, ::8],
+                        n_inst=np.array(len(r.scores)), scores=r.scores.numpy(), polygons=r.polygons.numpy(),
+                        recs=r.recs.numpy())
+    print("testr_full: instances", len(r.scores), "logit std", out["pred_logits"].std().item())
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["manifest", "unet", "sched", "msda", "merge", "testr"]
+    torch.manual_seed(0)
+    for w in what:
+        {"manifest": gen_manifest, "unet": gen_unet, "sched": gen_sched, "msda": gen_msda, "merge": gen_merge,
+         "testr": gen_testr}[w]()

@@ -1,0 +1,224 @@
+"""Parity of each sm_100a kernel (through the C ABI) against the oracle / a plain fp32 torch restatement.
+Integer/fp32-exact work (sampler update, tile blend) must be bit-identical; bf16 tensor-core work is checked
+against fp32 math on the same bf16-rounded inputs with a stated tolerance."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2  # max-abs error relative to max-abs of the reference, bf16 outputs (8 mantissa bits)
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_lib):
+    from tair_b200 import ops as o
+    return o
+
+
+def rn(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (4096, 320, 320), (1000, 320, 320), (1232, 640, 1024),
+                                   (16, 1280, 320), (300, 97, 256), (77, 2, 256), (5000, 1920, 640), (65, 8, 72)])
+def test_gemm_shapes(ops, M, N, K):
+    a, w = rn(M, K).bfloat16(), rn(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    out = ops.gemm(a, w)
+    assert rel(out, a.float() @ w.float().t()) < BF16_TOL
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 2048, 640, 320
+    a, w = rn(M, K).bfloat16(), rn(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    bias, res, rg = rn(N, seed=2), rn(M, N, seed=3).bfloat16(), rn(M // 512, N, seed=4)
+    base = a.float() @ w.float().t() + bias
+    assert rel(ops.gemm(a, w, bias=bias, residual=res), base + res.float()) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, rowgroup=rg, rows_per_group=512), base + rg.repeat_interleave(512, 0)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(base)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, act=ops.ACT_SILU), F.silu(base)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, act=ops.ACT_RELU), F.relu(base)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, out_dtype=torch.float32), base) < 1e-5
+    # strided output / strided A (column slices of wider buffers)
+    wide = torch.zeros(M, N + 64, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, out=wide[:, 64:])
+    assert rel(wide[:, 64:], base) < BF16_TOL and wide[:, :64].abs().max() == 0
+    a_wide = rn(M, K + 128, seed=7).bfloat16()
+    assert rel(ops.gemm(a_wide[:, 128:], w), a_wide[:, 128:].float() @ w.float().t()) < BF16_TOL
+
+
+def test_gemm_geglu_matches_chunked_reference(ops):
+    from tair_b200.model.attention import interleave_geglu
+    M, C = 1000, 320
+    a = rn(M, C).bfloat16()
+    w, b = rn(8 * C, C, scale=C ** -0.5, seed=1), rn(8 * C, seed=2)
+    wi, bi = interleave_geglu(w.bfloat16(), b)
+    out = ops.gemm(a, wi, bias=bi, act=ops.ACT_GEGLU)
+    val, gate = (a.float() @ w.bfloat16().float().t() + b).chunk(2, dim=-1)
+    assert rel(out, val * F.gelu(gate)) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,stride", [(1, 16, 64, 64, 1), (2, 64, 320, 320, 1), (2, 32, 640, 640, 1),
+                                                  (3, 8, 1280, 1280, 1), (1, 8, 2560, 1280, 1), (2, 64, 320, 4, 1),
+                                                  (2, 64, 320, 320, 2), (2, 16, 1280, 1280, 2), (1, 4, 64, 64, 1)])
+def test_conv3x3(ops, B, H, Cin, Cout, stride):
+    x = rn(B, Cin, H, H).bfloat16()
+    w = rn(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1).bfloat16()
+    bias = rn(Cout, seed=2)
+    out = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(),
+                      stride=stride, bias=bias)
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+    assert rel(out, ref) < BF16_TOL
+
+
+def test_conv3x3_fused_epilogue(ops):
+    B, H, C = 2, 32, 320
+    x = rn(B, C, H, H).bfloat16()
+    w = rn(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=1).bfloat16()
+    bias, emb, res = rn(C, seed=2), rn(B, C, seed=3), rn(B, H, H, C, seed=4).bfloat16()
+    out = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(C, -1).contiguous(), bias=bias,
+                      rowgroup=emb, rows_per_group=H * H, residual=res)
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1) + emb[:, :, None, None]
+    assert rel(out, ref.permute(0, 2, 3, 1) + res.float()) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 1, 128, 128), (2, 5, 1024, 1024), (2, 10, 1024, 77), (3, 20, 64, 64),
+                                       (3, 20, 64, 77), (1, 3, 200, 333), (1, 5, 4096, 4096)])
+def test_attention(ops, B, H, Lq, Lk):
+    C = H * 64
+    q, k, v = rn(B * Lq, C, scale=1.5).bfloat16(), rn(B * Lk, C, scale=1.5, seed=1).bfloat16(), rn(B * Lk, C, seed=2).bfloat16()
+    out = ops.attention(q, k, v, B=B, H=H, Lq=Lq, Lk=Lk)
+    def heads(t, L):
+        return t.float().view(B, L, H, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(heads(q, Lq), heads(k, Lk), heads(v, Lk)).transpose(1, 2).reshape(B * Lq, C)
+    assert torch.isfinite(out.float()).all() and rel(out, ref) < BF16_TOL
+
+
+def test_attention_fused_qkv_slices(ops):
+    B, H, L = 2, 5, 256
+    C = H * 64
+    qkv = rn(B * L, 3 * C).bfloat16()
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B=B, H=H, Lq=L, Lk=L)
+    def heads(t):
+        return t.float().reshape(B, L, H, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(heads(qkv[:, :C]), heads(qkv[:, C:2 * C]), heads(qkv[:, 2 * C:]))
+    assert rel(out, ref.transpose(1, 2).reshape(B * L, C)) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,HW,C,eps,act", [(2, 4096, 320, 1e-5, "silu"), (2, 1024, 640, 1e-6, "none"),
+                                            (3, 64, 2560, 1e-5, "silu"), (2, 1024, 1920, 1e-5, "silu"),
+                                            (2, 4096, 256, 1e-5, "gelu"), (2, 1024, 64, 1e-5, "silu"),
+                                            (1, 256, 192, 1e-5, "silu"), (2, 4096, 960, 1e-5, "silu")])
+def test_groupnorm(ops, B, HW, C, eps, act):
+    x = (rn(B, HW, C) * 1.7 + 0.4).bfloat16()
+    g, b = 1 + 0.1 * rn(C, seed=1), 0.1 * rn(C, seed=2)
+    a = {"silu": ops.ACT_SILU, "none": ops.ACT_NONE, "gelu": ops.ACT_GELU}[act]
+    out = ops.groupnorm(x, g, b, eps=eps, act=a)
+    ref = F.group_norm(x.float().transpose(1, 2), 32, g, b, eps).transpose(1, 2)
+    ref = {"silu": F.silu, "none": lambda t: t, "gelu": F.gelu}[act](ref)
+    assert rel(out, ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (333, 1280), (9472, 256), (7, 2048)])
+def test_layernorm(ops, M, C):
+    x = (rn(M, C) * 2 + 0.3).bfloat16()
+    g, b = 1 + 0.1 * rn(C, seed=1), 0.1 * rn(C, seed=2)
+    assert rel(ops.layernorm(x, g, b), F.layer_norm(x.float(), (C,), g, b, 1e-5)) < BF16_TOL
+
+
+def test_sampler_update_bit_exact_vs_oracle(ops):
+    from oracle import sampler
+    tabs = sampler.tables_to_torch(sampler.make_schedule(sampler.diffusion_betas(), 50), "cuda")
+    order = ["sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+             "posterior_variance"]
+    B = 16
+    x, v, vu, nz = (rn(B, 4, 64, 64, seed=s) for s in range(4))
+    for idx in (49, 25, 1, 0):
+        t = torch.full((B,), idx, device="cuda", dtype=torch.long)
+        ref, ref0 = sampler.p_sample_update(tabs, x, v, t, nz)
+        x0 = torch.empty_like(x)
+        out = ops.sampler_update(x, v, nz, t, [tabs[k] for k in order], pred_x0=x0)
+        assert torch.equal(out, ref) and torch.equal(x0, ref0), idx
+        ref_cfg, _ = sampler.p_sample_update(tabs, x, v, t, nz, v_uncond=vu, cfg_scale=4.0)
+        assert torch.equal(ops.sampler_update(x, v, nz, t, [tabs[k] for k in order], v_uncond=vu, cfg_scale=4.0), ref_cfg)
+    t = torch.randint(0, 50, (B,), device="cuda")  # per-sample indices (extract_into_tensor semantics)
+    assert torch.equal(ops.sampler_update(x, v, nz, t, [tabs[k] for k in order]), sampler.p_sample_update(tabs, x, v, t, nz)[0])
+
+
+def test_layout_and_elementwise(ops):
+    x = rn(3, 4, 64, 64)
+    nhwc = ops.nchw_to_nhwc(x, 64)
+    assert nhwc.shape == (3, 64, 64, 64) and nhwc[..., 4:].abs().max() == 0
+    assert torch.equal(nhwc[..., :4], x.permute(0, 2, 3, 1).bfloat16())
+    f = rn(2, 37, 24, 320).bfloat16()
+    assert torch.equal(ops.nhwc_to_nchw(f), f.float().permute(0, 3, 1, 2))
+    assert torch.equal(ops.nhwc_to_nchw(nhwc, 4), x.bfloat16().float())
+    a, b, c = rn(2, 8, 8, 640).bfloat16(), rn(2, 8, 8, 320, seed=1).bfloat16(), rn(2, 8, 8, 320, seed=2).bfloat16()
+    assert torch.equal(ops.concat_add(a, b, c), torch.cat([a, (b.float() + c.float()).bfloat16()], -1))
+    assert torch.equal(ops.concat_add(a, b), torch.cat([a, b], -1))
+    assert torch.equal(ops.add(b, c), (b.float() + c.float()).bfloat16())
+    up = ops.upsample2x(b)
+    assert torch.equal(up, F.interpolate(b.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).bfloat16())
+    t = torch.tensor([0, 20, 500, 999], device="cuda")
+    from oracle.unet import timestep_embedding
+    assert (ops.timestep_embedding(t, 320).float() - timestep_embedding(t, 320)).abs().max() < 1e-2
+
+
+def test_msda_forward_vs_oracle_and_fixture(ops, golden):
+    from oracle import msda, weights
+    g = golden("msda_case.npz")
+    shapes = [tuple(int(v) for v in r) for r in g["shapes"]]
+    S = sum(h * w for h, w in shapes)
+    B, M, D, Lq, L, P = 2, 8, 32, 24, 3, 4
+    value = weights.seeded_randn((B, S, M, D), 21).cuda()
+    loc = (torch.rand((B, Lq, M, L, P, 2), generator=torch.Generator().manual_seed(22)) * 1.4 - 0.2).cuda()
+    w = torch.softmax(weights.seeded_randn((B, Lq, M, L * P), 23), -1).view(B, Lq, M, L, P).cuda()
+    shp = torch.tensor(shapes, device="cuda", dtype=torch.long)
+    start = torch.cat([shp.new_zeros(1), (shp[:, 0] * shp[:, 1]).cumsum(0)[:-1]])
+    out = ops.msda_forward(value, shp, start, loc, w)
+    assert (out.cpu().numpy() - g["out"]).__abs__().max() < 1e-5           # reference fixture, fp32 mode
+    # TESTR geometry (4 levels, 9472 tokens) against the oracle, fp32 and bf16 value
+    shapes = [(16, 16), (32, 32), (64, 64), (64, 64)]
+    S = 9472
+    B, Lq = 2, 700
+    value, loc = rn(B, S, 8, 32), torch.rand(B, Lq, 8, 4, 4, 2, device="cuda") * 1.2 - 0.1
+    w = torch.softmax(rn(B, Lq, 8, 16, seed=1), -1).view(B, Lq, 8, 4, 4)
+    shp = torch.tensor(shapes, device="cuda", dtype=torch.long)
+    start = torch.cat([shp.new_zeros(1), (shp[:, 0] * shp[:, 1]).cumsum(0)[:-1]])
+    ref = msda.msda_core(value, shapes, loc, w)
+    assert (ops.msda_forward(value, shp, start, loc, w) - ref).abs().max() < 1e-5
+    vb = value.bfloat16()
+    refb = msda.msda_core(vb.float(), shapes, loc, w)
+    assert rel(ops.msda_forward(vb, shp, start, loc, w, out_dtype=torch.bfloat16), refb) < BF16_TOL
+
+
+@pytest.mark.parametrize("oh,ow", [(200, 300), (128, 128), (130, 250), (512, 512)])
+def test_blend_tiles_bit_exact(ops, oh, ow):
+    from oracle import tiles
+    n_h, n_w, _, _ = tiles.tile_grid(oh, ow)
+    g = torch.Generator().manual_seed(31)
+    tl = [torch.rand((1, 3, 512, 512), generator=g) for _ in range(n_h * n_w)]
+    ref = tiles.merge_tiles(tl, (oh, ow))
+    out = ops.blend_tiles(torch.cat(tl).cuda(), n_h, n_w, 64, 4 * oh, 4 * ow)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_blend_tiles_fixture_and_ragged_list(ops, golden):
+    from oracle import tiles
+    g = golden("merge_case.npz")
+    oh, ow, n = (int(v) for v in g["a_size"])
+    gen = torch.Generator().manual_seed(31)
+    tl = torch.cat([torch.rand((1, 3, 512, 512), generator=gen) for _ in range(n)]).cuda()
+    out = ops.blend_tiles(tl, 2, 3, 64, 4 * oh, 4 * ow)
+    assert np.array_equal(out[0, :, ::37, ::41].cpu().numpy(), g["a_sample"])
+    # fewer tiles than grid cells: the reference stops placing tiles and divides by clamp(weight, 1e-8)
+    short = [t[None] for t in tl[:4].cpu()]
+    ref = tiles.merge_tiles(short, (oh, ow))
+    assert torch.equal(ops.blend_tiles(tl[:4].contiguous(), 2, 3, 64, 4 * oh, 4 * ow).cpu(), ref)
