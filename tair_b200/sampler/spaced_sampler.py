@@ -1,0 +1,233 @@
+"""Spaced DDPM ancestral sampler driving the sm_100a denoising step.
+
+Drop-in surface of terediff/sampler/sampler.py:10-38 (``Sampler``) and spaced_sampler.py:67-328
+(``SpacedSampler``): ``make_schedule``, ``apply_model``, ``p_sample``, ``sample``, ``val_sample`` keep their
+argument lists and return values.  Differences, all behaviour-preserving on the reference's working paths:
+
+* the per-step arithmetic (x0 from v, posterior mean/variance, noise injection, optional CFG combine) is ONE
+  kernel (``tair_sampler_update``) instead of ~9 elementwise launches, bit-identical in fp32;
+* classifier-free guidance actually works: the reference's CFG branch does arithmetic on ``(eps, feats)`` tuples
+  and raises (spaced_sampler.py:161-163, SURVEY.md §8a hazard 6).  Here cond/uncond are evaluated as one
+  stacked batch, v = v_u + s (v_c - v_u), features are taken from the cond half;
+* ``val_sample`` accepts B > 1 tiles: the reference builds the prompt from ``results[0]`` only (:298) and therefore
+  is batch-1 in practice; here every tile gets its own prompt (for B == 1 this is the reference behaviour);
+* the whole step (ControlNet + UNet + update [+ TESTR head]) can be captured once in a CUDA graph and replayed
+  (``use_cuda_graph``), removing the several thousand eager launches per step of the reference;
+* step noise comes from ``noise_fn(i, x)`` when given (parity tests inject the oracle's noise), else randn_like.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+
+_TABLES = ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+           "posterior_variance")
+
+
+def space_timesteps(num_timesteps: int, section_counts) -> set:
+    """Evenly spaced subset of the training timesteps (spaced_sampler.py:14-65; 'ddimN' striding included)."""
+    if isinstance(section_counts, str):
+        if section_counts.startswith("ddim"):
+            want = int(section_counts[4:])
+            for stride in range(1, num_timesteps):
+                picked = range(0, num_timesteps, stride)
+                if len(picked) == want:
+                    return set(picked)
+            raise ValueError(f"cannot create exactly {num_timesteps} steps with an integer stride")
+        section_counts = [int(v) for v in section_counts.split(",")]
+    base, extra = divmod(num_timesteps, len(section_counts))
+    steps, offset = [], 0
+    for k, count in enumerate(section_counts):
+        size = base + (1 if k < extra else 0)
+        if size < count:
+            raise ValueError(f"cannot divide section of {size} steps into {count}")
+        stride = 1 if count <= 1 else (size - 1) / (count - 1)
+        pos = 0.0
+        for _ in range(count):
+            steps.append(offset + round(pos))
+            pos += stride
+        offset += size
+    return set(steps)
+
+
+class Sampler(nn.Module):
+    """sampler.py:10-38."""
+
+    def __init__(self, betas: np.ndarray, parameterization: str, rescale_cfg: bool):
+        super().__init__()
+        self.num_timesteps = len(betas)
+        self.training_betas = betas
+        self.training_alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+        self.context = {}
+        self.parameterization = parameterization
+        self.rescale_cfg = rescale_cfg
+
+    def register(self, name: str, value: np.ndarray, dtype: torch.dtype = torch.float32) -> None:
+        self.register_buffer(name, torch.tensor(value, dtype=dtype))
+
+    def get_cfg_scale(self, default_cfg_scale: float, model_t: int) -> float:
+        if self.rescale_cfg and default_cfg_scale > 1:
+            return 1 + default_cfg_scale * ((1 - math.cos(math.pi * ((1000 - model_t) / 1000) ** 5.0)) / 2)
+        return default_cfg_scale
+
+
+class SpacedSampler(Sampler):
+    def __init__(self, betas: np.ndarray, parameterization: str = "v", rescale_cfg: bool = False):
+        super().__init__(betas, parameterization, rescale_cfg)
+        if parameterization != "v":
+            raise NotImplementedError("tair_b200 implements the v-parameterisation used by TeReDiff (val_patches.py:241)")
+        self.noise_fn: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None
+        self._graphs: Dict[tuple, "_StepGraph"] = {}
+
+    # ---- schedule (host, float64; spaced_sampler.py:77-121) -------------------------------------------------
+    def make_schedule(self, num_steps: int) -> None:
+        keep = sorted(space_timesteps(self.num_timesteps, str(num_steps)))
+        abar_kept = self.training_alphas_cumprod[keep]
+        prev_kept = np.concatenate([[1.0], abar_kept[:-1]])
+        betas = 1 - abar_kept / prev_kept
+        self.timesteps = np.array(keep, dtype=np.int32)
+        alphas = 1.0 - betas
+        abar = np.cumprod(alphas, axis=0)
+        abar_prev = np.append(1.0, abar[:-1])
+        with np.errstate(divide="ignore"):
+            var = betas * (1.0 - abar_prev) / (1.0 - abar)
+            self.register("sqrt_alphas_cumprod", np.sqrt(abar))
+            self.register("sqrt_one_minus_alphas_cumprod", np.sqrt(1 - abar))
+            self.register("sqrt_recip_alphas_cumprod", np.sqrt(1.0 / abar))        # inf at the last step: never used for 'v'
+            self.register("sqrt_recipm1_alphas_cumprod", np.sqrt(1.0 / abar - 1))
+            self.register("posterior_variance", var)
+            tail = var[1] if len(var) > 1 else var[0]
+            self.register("posterior_log_variance_clipped", np.log(np.append(tail, var[1:] if len(var) > 1 else var[:1])))
+            self.register("posterior_mean_coef1", betas * np.sqrt(abar_prev) / (1.0 - abar))
+            self.register("posterior_mean_coef2", (1.0 - abar_prev) * np.sqrt(alphas) / (1.0 - abar))
+
+    def _tables(self) -> List[torch.Tensor]:
+        return [getattr(self, n) for n in _TABLES]
+
+    # ---- one step ------------------------------------------------------------------------------------------
+    def apply_model(self, model, x, model_t, cond, uncond, cfg_scale):
+        """-> (v_cond, v_uncond | None, feats).  cfg == 1 or no uncond: single forward (spaced_sampler.py:158-159)."""
+        if uncond is None or cfg_scale == 1.0:
+            v, feats = model(x, model_t, cond)
+            return v, None, feats
+        B = x.shape[0]
+        both = {k: torch.cat([cond[k], uncond[k]], 0) for k in cond}
+        v, feats = model(torch.cat([x, x], 0), torch.cat([model_t, model_t], 0), both)
+        return v[:B].contiguous(), v[B:].contiguous(), [f[:B] for f in feats]
+
+    @torch.no_grad()
+    def p_sample(self, model, x, model_t, t, cond, uncond, cfg_scale, noise: Optional[torch.Tensor] = None):
+        v, v_u, feats = self.apply_model(model, x, model_t, cond, uncond, cfg_scale)
+        if noise is None:
+            noise = torch.randn_like(x)
+        x_prev = ops.sampler_update(x.contiguous(), v.contiguous(), noise.contiguous(), t, self._tables(),
+                                    v_uncond=v_u, cfg_scale=float(cfg_scale))
+        return x_prev, feats
+
+    def _noise(self, i: int, x: torch.Tensor) -> torch.Tensor:
+        return self.noise_fn(i, x) if self.noise_fn is not None else torch.randn_like(x)
+
+    # ---- loops ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, model, device, steps, x_size, cond, uncond, cfg_scale, tiled=False, tile_size=-1, tile_stride=-1,
+               x_T=None, progress=True, cfg=None, use_cuda_graph: bool = False):
+        """spaced_sampler.py:192-243 -> (x, sampled_unet_feats)."""
+        if tiled:
+            raise NotImplementedError("latent tiling (make_tiled_fn) is not on the val_patches path")
+        self.make_schedule(steps)
+        self.to(device)
+        x = torch.randn(x_size, device=device, dtype=torch.float32) if x_T is None else x_T.to(device).float()
+        order = np.flip(self.timesteps)
+        total = len(order)
+        bs = x_size[0]
+        want = [] if cfg is None else list(cfg.exp_args["unet_feat_sampling_timestep"])
+        kept = []
+        stepper = _StepGraph(self, model, x, cond, uncond) if use_cuda_graph else None
+        for i, cur in enumerate(order):
+            cur = int(cur)
+            scale = self.get_cfg_scale(cfg_scale, cur)
+            if stepper is not None:
+                x, feats = stepper.run(x, cur, total - i - 1, self._noise(i, x), scale)
+            else:
+                model_t = torch.full((bs,), cur, device=device, dtype=torch.long)
+                t = torch.full((bs,), total - i - 1, device=device, dtype=torch.long)
+                x, feats = self.p_sample(model, x, model_t, t, cond, uncond, scale, noise=self._noise(i, x))
+            if i + 1 in want:
+                kept.append((i + 1, cur, [f.clone() for f in feats] if stepper is not None else feats))
+        return x, kept
+
+    @torch.no_grad()
+    def val_sample(self, model, device, steps, x_size, cond, uncond, cfg_scale, tiled=False, tile_size=-1,
+                   tile_stride=-1, x_T=None, progress=True, cfg=None, pure_cldm=None, ts_model=None, val_prompt=None):
+        """spaced_sampler.py:246-328 -> (x, ts_results): every step runs the text-spotting head on the step's decoder
+        features, decodes the recognised strings and re-encodes the prompt that conditions the NEXT step."""
+        from ..prompt import build_prompt, decode_texts
+        assert ts_model is not None, "Text-spotting model must be provided for validation sampling."
+        self.make_schedule(steps)
+        self.to(device)
+        x = torch.randn(x_size, device=device, dtype=torch.float32) if x_T is None else x_T.to(device).float()
+        order = np.flip(self.timesteps)
+        total = len(order)
+        bs = x_size[0]
+        mode = cfg.exp_args.mode if cfg is not None else "VAL"
+        style = cfg.exp_args.prompt_style if cfg is not None else "CAPTION"
+        ts_results = []
+        for i, cur in enumerate(order):
+            cur = int(cur)
+            model_t = torch.full((bs,), cur, device=device, dtype=torch.long)
+            t = torch.full((bs,), total - i - 1, device=device, dtype=torch.long)
+            x, feats = self.p_sample(model, x, model_t, t, cond, uncond, self.get_cfg_scale(cfg_scale, cur),
+                                     noise=self._noise(i, x))
+            _, results = ts_model(feats, None, mode)
+            texts, polys = decode_texts(results)                       # one D2H copy for the whole batch
+            prompts = [build_prompt(tx, style) for tx in texts]
+            cond["c_txt"] = pure_cldm.clip.encode(prompts if bs > 1 else prompts[0])   # mutated in place like :317
+            ts_results.append(dict(timestep=cur, pred_texts=texts[0], pred_prompt=prompts[0], pred_polys=polys[0],
+                                   batch_texts=texts, batch_prompts=prompts))
+        return x, ts_results
+
+
+class _StepGraph:
+    """One denoising step (model forward(s) + sampler update) captured in a CUDA graph and replayed per step.
+    Static inputs: x, model_t, t, noise, cond tensors; cfg scale is baked per distinct value."""
+
+    def __init__(self, sampler: SpacedSampler, model, x, cond, uncond):
+        self.s, self.model = sampler, model
+        self.x = x.clone()
+        B = x.shape[0]
+        self.model_t = torch.zeros((B,), device=x.device, dtype=torch.long)
+        self.t = torch.zeros((B,), device=x.device, dtype=torch.long)
+        self.noise = torch.zeros_like(x)
+        self.cond = {k: v.clone() for k, v in cond.items()}
+        self.uncond = None if uncond is None else {k: v.clone() for k, v in uncond.items()}
+        self.graphs: Dict[float, tuple] = {}
+
+    def _capture(self, scale: float):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture: weight packing, smem attributes, allocator
+            for _ in range(2):
+                self.s.p_sample(self.model, self.x, self.model_t, self.t, self.cond, self.uncond, scale, noise=self.noise)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out, feats = self.s.p_sample(self.model, self.x, self.model_t, self.t, self.cond, self.uncond, scale,
+                                         noise=self.noise)
+        self.graphs[scale] = (g, out, feats)
+
+    def run(self, x, model_t: int, t: int, noise, scale: float):
+        if scale not in self.graphs:
+            self._capture(scale)
+        g, out, feats = self.graphs[scale]
+        self.x.copy_(x)
+        self.model_t.fill_(model_t)
+        self.t.fill_(t)
+        self.noise.copy_(noise)
+        g.replay()
+        return out.clone(), feats
