@@ -17,6 +17,49 @@ from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, Epilogue, T
 BF16 = torch.bfloat16
 
 
+class KernelTimer:
+    """Optional per-family CUDA-event timing of the launches issued through this module (used by bench.py to
+    measure the dominant kernel live, on the launching stream).  Off by default: zero overhead on the hot path."""
+
+    def __init__(self):
+        self.records = {}   # family -> list of (start_event, end_event, work)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            out[fam] = dict(launches=len(recs), ms=ms, work=sum(w for _, _, w in recs))
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_timer(t: Optional[KernelTimer]) -> None:
+    global _timer
+    _timer = t
+
+
+class _timed:
+    __slots__ = ("fam", "work", "a")
+
+    def __init__(self, fam: str, work: float):
+        self.fam, self.work = fam, work
+
+    def __enter__(self):
+        if _timer is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _timer.records.setdefault(self.fam, []).append((self.a, b, self.work))
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -85,7 +128,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
     e = _make_epilogue(out, M, n_out, bias, residual, rowgroup, rows_per_group, act)
-    rc = _lib.lib().tair_gemm_bf16(a2.data_ptr(), lda, w2.data_ptr(), ldw, M, N, K, C.byref(e), _stream())
+    with _timed("gemm", 2.0 * M * N * K):
+        rc = _lib.lib().tair_gemm_bf16(a2.data_ptr(), lda, w2.data_ptr(), ldw, M, N, K, C.byref(e), _stream())
     _lib.check(rc, "tair_gemm_bf16")
     return out
 
@@ -108,7 +152,8 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, bias=None, res
     o2 = out.view(M, -1) if out.dim() == 4 else out
     r2 = residual.view(M, -1) if (residual is not None and residual.dim() == 4) else residual
     e = _make_epilogue(o2, M, Cout, bias, r2, rowgroup, rows_per_group, act)
-    rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, C.byref(e), _stream())
+    with _timed("conv3x3", 2.0 * M * Cout * 9 * Cin):
+        rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, C.byref(e), _stream())
     _lib.check(rc, "tair_conv3x3_bf16")
     return out
 
@@ -140,8 +185,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, H: i
     o2, ldo = _rows(out, "out")
     if scale is None:
         scale = head_dim ** -0.5
-    rc = _lib.lib().tair_attention_bf16(q2.data_ptr(), ldq, k2.data_ptr(), ldk, v2.data_ptr(), ldv, o2.data_ptr(), ldo,
-                                        B, H, Lq, Lk, head_dim, float(scale), _stream())
+    with _timed("attention", 4.0 * B * H * Lq * Lk * head_dim):
+        rc = _lib.lib().tair_attention_bf16(q2.data_ptr(), ldq, k2.data_ptr(), ldk, v2.data_ptr(), ldv, o2.data_ptr(),
+                                            ldo, B, H, Lq, Lk, head_dim, float(scale), _stream())
     _lib.check(rc, "tair_attention_bf16")
     return out
 
@@ -173,8 +219,9 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, group
     if out is None:
         out = torch.empty_like(x)
     ws = _gn_workspace(x.device, B, groups)
-    rc = _lib.lib().tair_groupnorm_nhwc(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, HW, C,
-                                        groups, float(eps), act, ws.data_ptr(), _stream())
+    with _timed("groupnorm", 6.0 * x.numel()):  # bytes: two reads + one write of a bf16 tensor
+        rc = _lib.lib().tair_groupnorm_nhwc(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, HW, C,
+                                            groups, float(eps), act, ws.data_ptr(), _stream())
     _lib.check(rc, "tair_groupnorm_nhwc")
     return out
 
@@ -186,8 +233,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     if out is None:
         out = torch.empty((x2.shape[0], x2.shape[1]), device=x.device, dtype=BF16)
     o2, ldy = _rows(out, "out")
-    rc = _lib.lib().tair_layernorm(x2.data_ptr(), ldx, o2.data_ptr(), ldy, gamma.data_ptr(), beta.data_ptr(),
-                                   x2.shape[0], x2.shape[1], float(eps), _stream())
+    with _timed("layernorm", 4.0 * x2.numel()):  # bytes: one read + one write
+        rc = _lib.lib().tair_layernorm(x2.data_ptr(), ldx, o2.data_ptr(), ldy, gamma.data_ptr(), beta.data_ptr(),
+                                       x2.shape[0], x2.shape[1], float(eps), _stream())
     _lib.check(rc, "tair_layernorm")
     return out
 

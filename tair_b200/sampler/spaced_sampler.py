@@ -69,7 +69,12 @@ class Sampler(nn.Module):
         self.rescale_cfg = rescale_cfg
 
     def register(self, name: str, value: np.ndarray, dtype: torch.dtype = torch.float32) -> None:
-        self.register_buffer(name, torch.tensor(value, dtype=dtype))
+        new = torch.tensor(value, dtype=dtype)
+        old = getattr(self, name, None)
+        if isinstance(old, torch.Tensor) and old.shape == new.shape and old.dtype == new.dtype:
+            old.copy_(new)  # keep the device address stable: captured CUDA graphs read these tables
+        else:
+            self.register_buffer(name, new)
 
     def get_cfg_scale(self, default_cfg_scale: float, model_t: int) -> float:
         if self.rescale_cfg and default_cfg_scale > 1:
@@ -148,7 +153,13 @@ class SpacedSampler(Sampler):
         bs = x_size[0]
         want = [] if cfg is None else list(cfg.exp_args["unet_feat_sampling_timestep"])
         kept = []
-        stepper = _StepGraph(self, model, x, cond, uncond) if use_cuda_graph else None
+        stepper = None
+        if use_cuda_graph:
+            key = (id(model), tuple(x.shape), uncond is None, tuple(sorted((k, tuple(v.shape)) for k, v in cond.items())))
+            stepper = self._graphs.get(key)
+            if stepper is None:
+                stepper = self._graphs[key] = _StepGraph(self, model, x, cond, uncond)
+            stepper.load_cond(cond, uncond)
         for i, cur in enumerate(order):
             cur = int(cur)
             scale = self.get_cfg_scale(cfg_scale, cur)
@@ -220,6 +231,13 @@ class _StepGraph:
             out, feats = self.s.p_sample(self.model, self.x, self.model_t, self.t, self.cond, self.uncond, scale,
                                          noise=self.noise)
         self.graphs[scale] = (g, out, feats)
+
+    def load_cond(self, cond, uncond):
+        for k, v in cond.items():
+            self.cond[k].copy_(v)
+        if uncond is not None:
+            for k, v in uncond.items():
+                self.uncond[k].copy_(v)
 
     def run(self, x, model_t: int, t: int, noise, scale: float):
         if scale not in self.graphs:
