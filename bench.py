@@ -301,8 +301,8 @@ def main():
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(world, use_graph),
             "unet_step_latency_ms": step_ms,
-            "model_tflops": GFLOP_PER_TILE_STEP * BATCH / step_ms / 1e3,
-            "model_frac_of_tensor_peak": GFLOP_PER_TILE_STEP * BATCH / step_ms / 1e3 / pk["tc_sustained"],
+            "model_tflops": GFLOP_PER_TILE_STEP * BATCH / step_ms,
+            "model_frac_of_tensor_peak": GFLOP_PER_TILE_STEP * BATCH / step_ms / pk["tc_sustained"],
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches_per_step * SAMPLER_STEPS * K),
