@@ -68,8 +68,10 @@ typedef struct tair_epilogue {
   const float* bias;       /* [N] fp32 or NULL                                         */
   const void* residual;    /* [M, ldr] bf16 added after the activation, or NULL        */
   int64_t ldr;
-  const float* rowgroup;   /* [ceil(M/rows_per_group), ldg] fp32 added before act, or NULL
-                              (timestep-embedding add: one row per image)              */
+  const float* rowgroup;   /* fp32 [G, ldg] added before act, or NULL.  rows_per_group > 0: row m uses
+                              rowgroup[m / rows_per_group] (timestep-embedding add: one row per image);
+                              rows_per_group < 0: periodic, row m uses rowgroup[m % -rows_per_group]
+                              (positional-embedding projections shared by every image)     */
   int64_t ldg;
   int32_t rows_per_group;
   int32_t reserved;
@@ -144,6 +146,23 @@ int tair_msda_forward(const void* value, const int64_t* spatial_shapes, const in
  * overlap (stride = tile - overlap) into out [C, out_h, out_w] (top-left crop of the canvas). */
 int tair_blend_tiles(const float* tiles, float* out, int32_t n_tiles, int32_t n_h, int32_t n_w, int32_t C,
                      int32_t tile, int32_t overlap, int32_t out_h, int32_t out_w, void* stream);
+
+/* MSDeformAttn core fused with its pre-processing (ms_deform_attn.py:136-149): proj rows hold the raw
+ * sampling_offsets (M*L*P*2) followed by the raw attention logits (M*L*P) of one query; the kernel applies the
+ * softmax over L*P and forms loc = ref + offset/(W,H) (ref_dim 2) or ref_xy + offset/P * ref_wh * 0.5 (ref_dim 4).
+ * ref is fp32 [(B,) Lq/q_per_ref, L, ref_dim]; ref_batch_stride (elements) is 0 when shared by all images.
+ * value bf16 [B,S,M,D] -> out bf16 [B*Lq, M*D]. */
+int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                    const float* proj, int64_t ldp, const float* ref, int32_t ref_dim, int64_t ref_batch_stride,
+                    int32_t q_per_ref, void* out, int32_t B, int32_t S, int32_t M, int32_t D, int32_t L,
+                    int32_t Lq, int32_t P, void* stream);
+
+/* Short-sequence multi-head attention (nn.MultiheadAttention core, head_dim 32, L <= 128) on the fused in_proj
+ * output qkv [rows, ld] (q | k | v, each H*32 wide); sequence (o, i), o < n_outer, i < n_inner, starts at row
+ * o*outer_stride + i*inner_stride and its tokens are tok_stride rows apart.  out [rows, ldo] uses the same rows. */
+int tair_mha_small(const void* qkv, int64_t ld, void* out, int64_t ldo, int32_t H, int32_t head_dim, int32_t L,
+                   int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride, int64_t tok_stride,
+                   float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -119,7 +119,8 @@ template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn, bool row_ok, uint32_t taddr) {
   const tair_epilogue& e = p.epi;
       const float* rg = nullptr;
-      if (e.rowgroup != nullptr && row_ok) rg = e.rowgroup + (int64_t)(m / e.rows_per_group) * e.ldg;
+      if (e.rowgroup != nullptr && row_ok)
+        rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
 
       if constexpr (ACT == TAIR_ACT_GEGLU) {
         constexpr int HALF = BN / 2;
@@ -398,7 +399,7 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   TAIR_REQUIRE(e != nullptr && e->out != nullptr, "epilogue/out pointer is NULL");
   TAIR_REQUIRE(e->ldc >= n_out, "ldc (%lld) < output columns (%d)", (long long)e->ldc, n_out);
   TAIR_REQUIRE(e->act >= 0 && e->act <= TAIR_ACT_RELU, "unknown activation %d", e->act);
-  if (e->rowgroup) TAIR_REQUIRE(e->rows_per_group > 0, "rows_per_group must be > 0");
+  if (e->rowgroup) TAIR_REQUIRE(e->rows_per_group != 0, "rows_per_group must be non-zero");
   if (e->act == TAIR_ACT_GEGLU)
     TAIR_REQUIRE(e->rowgroup == nullptr, "GEGLU epilogue does not take a row-group add");
   p.epi = *e;

@@ -107,6 +107,100 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaParams p) {
   }
 }
 
+
+// ---- fused variant: softmax over the L*P logits and the sampling-location arithmetic of
+// MSDeformAttn.forward (testr/adet/layers/ms_deform_attn.py:136-149) are done in the kernel, straight from the
+// fused [sampling_offsets | attention_weights] projection row, so no location / weight tensor is materialised.
+struct MsdaFusedParams {
+  const __nv_bfloat16* value;  // [B,S,M,D]
+  const int64_t* shapes;
+  const int64_t* starts;
+  const float* proj;           // [B*Lq, ldp]: M*L*P*2 offsets then M*L*P logits
+  int64_t ldp;
+  const float* ref;            // [ (B) , Lq/q_per_ref, L, ref_dim ]
+  int64_t ref_batch_stride;    // elements; 0 = reference points shared by all images
+  int ref_dim, q_per_ref;
+  __nv_bfloat16* out;          // [B*Lq, M*D]
+  int B, S, M, D, L, Lq, P;
+  int lanes_per_item;
+  long items;
+};
+
+constexpr int MSDA_MAX_LP = 32;
+
+template <int LT, int PT>  // compile-time (levels, points) or 0 for runtime loops
+__global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p) {
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long item = gtid / p.lanes_per_item;
+  const int part = (int)(gtid - item * p.lanes_per_item);
+  if (item >= p.items) return;
+  const int m = (int)(item % p.M);
+  const long bq = item / p.M;
+  const int b = (int)(bq / p.Lq);
+  const int q = (int)(bq - (long)b * p.Lq);
+  const int nL = LT > 0 ? LT : p.L, nP = PT > 0 ? PT : p.P;
+  const int LP = nL * nP;
+  const float* row = p.proj + bq * p.ldp;
+  const float* offp = row + (long)m * LP * 2;
+  const float* logit = row + (long)p.M * LP * 2 + (long)m * LP;
+  // softmax over the L*P logits of this (query, head)
+  float w[LT > 0 ? LT * PT : MSDA_MAX_LP];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int i = 0; i < (LT > 0 ? LT * PT : MSDA_MAX_LP); ++i)
+    if (i < LP) { w[i] = __ldg(logit + i); mx = fmaxf(mx, w[i]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < (LT > 0 ? LT * PT : MSDA_MAX_LP); ++i)
+    if (i < LP) { w[i] = __expf(w[i] - mx); sum += w[i]; }
+  const float inv = 1.f / sum;
+  const float* refq = p.ref + (long)b * p.ref_batch_stride + (long)(q / p.q_per_ref) * p.L * p.ref_dim;
+  const __nv_bfloat16* vbase = p.value + ((long)b * p.S * p.M + m) * p.D + part * 8;
+  const long row_stride = (long)p.M * p.D;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int l = 0; l < (LT > 0 ? LT : 8); ++l) {
+    if (l >= nL) break;
+    const int H = (int)__ldg(p.shapes + 2 * l), W = (int)__ldg(p.shapes + 2 * l + 1);
+    const __nv_bfloat16* vl = vbase + (long)__ldg(p.starts + l) * row_stride;
+    const float rx = __ldg(refq + l * p.ref_dim), ry = __ldg(refq + l * p.ref_dim + 1);
+    float sx, sy;  // offset scale: 1/(W,H) for points, box_wh * 0.5 / P for boxes (ms_deform_attn.py:139-146)
+    if (p.ref_dim == 2) { sx = 1.f / (float)W; sy = 1.f / (float)H; }
+    else { sx = __ldg(refq + l * p.ref_dim + 2) * 0.5f / (float)nP; sy = __ldg(refq + l * p.ref_dim + 3) * 0.5f / (float)nP; }
+#pragma unroll
+    for (int s = 0; s < (PT > 0 ? PT : 8); ++s) {
+      if (s >= nP) break;
+      const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + l * nP + s);
+      const float aw = w[l * nP + s] * inv;
+      const float h_im = (ry + off.y * sy) * (float)H - 0.5f;
+      const float w_im = (rx + off.x * sx) * (float)W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+        const int h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        float v1[8], v2[8], v3[8], v4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v1[i] = 0.f; v2[i] = 0.f; v3[i] = 0.f; v4[i] = 0.f; }
+        const bool top = h_low >= 0, bot = h_high <= H - 1, left = w_low >= 0, right = w_high <= W - 1;
+        if (top && left) load_vec8<__nv_bfloat16>(vl + ((long)h_low * W + w_low) * row_stride, v1);
+        if (top && right) load_vec8<__nv_bfloat16>(vl + ((long)h_low * W + w_high) * row_stride, v2);
+        if (bot && left) load_vec8<__nv_bfloat16>(vl + ((long)h_high * W + w_low) * row_stride, v3);
+        if (bot && right) load_vec8<__nv_bfloat16>(vl + ((long)h_high * W + w_high) * row_stride, v4);
+        const float w1 = hh * hw * aw, w2 = hh * lw * aw, w3 = lh * hw * aw, w4 = lh * lw * aw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
+      }
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(p.out + item * p.D + part * 8) = o;
+}
+
 }  // namespace
 }  // namespace tair
 
@@ -141,4 +235,33 @@ extern "C" int tair_msda_forward(const void* value, const int64_t* spatial_shape
   else msda_fwd_kernel<float, float><<<(unsigned)grid, block, 0, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("msda_fwd_kernel");
+}
+
+extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                               const float* proj, int64_t ldp, const float* ref, int32_t ref_dim,
+                               int64_t ref_batch_stride, int32_t q_per_ref, void* out, int32_t B, int32_t S,
+                               int32_t M, int32_t D, int32_t L, int32_t Lq, int32_t P, void* stream) {
+  TAIR_REQUIRE(value && spatial_shapes && level_start_index && proj && ref && out, "msda_fused: NULL pointer");
+  TAIR_REQUIRE(B > 0 && S > 0 && M > 0 && D > 0 && L > 0 && Lq > 0 && P > 0 && q_per_ref > 0, "msda_fused: bad shape");
+  TAIR_REQUIRE(ref_dim == 2 || ref_dim == 4, "msda_fused: reference points must have 2 or 4 coordinates");
+  TAIR_REQUIRE(L * P <= MSDA_MAX_LP && L <= 8 && P <= 8, "msda_fused: needs L <= 8, P <= 8, L*P <= %d", MSDA_MAX_LP);
+  TAIR_REQUIRE(D % 8 == 0 && D <= 256 && (32 % (D / 8)) == 0, "msda_fused: unsupported channels per head %d", D);
+  TAIR_REQUIRE(ldp >= (int64_t)M * L * P * 3 && ldp % 2 == 0, "msda_fused: projection row too short");
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(value) % 16) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(proj) % 8) == 0, "msda_fused: misaligned tensor");
+  MsdaFusedParams p{};
+  p.value = reinterpret_cast<const __nv_bfloat16*>(value);
+  p.shapes = spatial_shapes; p.starts = level_start_index;
+  p.proj = proj; p.ldp = ldp; p.ref = ref; p.ref_dim = ref_dim; p.ref_batch_stride = ref_batch_stride;
+  p.q_per_ref = q_per_ref; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.B = B; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P;
+  p.lanes_per_item = D / 8;
+  p.items = (long)B * Lq * M;
+  const long threads_total = p.items * p.lanes_per_item;
+  const long grid = (threads_total + 255) / 256;
+  TAIR_REQUIRE(grid < (1l << 31), "msda_fused: problem too large");
+  if (L == 4 && P == 4) msda_fused_kernel<4, 4><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else msda_fused_kernel<0, 0><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("msda_fused_kernel");
 }

@@ -108,7 +108,8 @@ def _make_epilogue(out, M, n_out, bias, residual, rowgroup, rows_per_group, act)
     if rowgroup is not None:
         _cuda(rowgroup, "rowgroup", torch.float32)
         g2, ldg = _rows(rowgroup, "rowgroup")
-        if rows_per_group <= 0 or g2.shape[0] * rows_per_group < M or g2.shape[1] < n_out:
+        covered = g2.shape[0] * rows_per_group >= M if rows_per_group > 0 else (rows_per_group < 0 and g2.shape[0] >= -rows_per_group)
+        if not covered or g2.shape[1] < n_out:
             raise TairError("rowgroup shape does not cover the output")
         e.rowgroup, e.ldg, e.rows_per_group = g2.data_ptr(), ldg, rows_per_group
     return e
@@ -365,4 +366,45 @@ def blend_tiles(tiles: torch.Tensor, n_h: int, n_w: int, overlap: int, out_h: in
     out = torch.empty((1, Cc, out_h, out_w), device=tiles.device, dtype=torch.float32)
     rc = _lib.lib().tair_blend_tiles(tiles.data_ptr(), out.data_ptr(), P_, n_h, n_w, Cc, T, overlap, out_h, out_w, _stream())
     _lib.check(rc, "tair_blend_tiles")
+    return out
+
+
+def msda_fused(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor, proj: torch.Tensor,
+               ref: torch.Tensor, *, B: int, Lq: int, n_heads: int, n_levels: int, n_points: int,
+               q_per_ref: int = 1, ref_shared: bool = False) -> torch.Tensor:
+    """value bf16 [B,S,M,D]; proj fp32 [B*Lq, >= M*L*P*3] (raw offsets then raw logits); ref fp32
+    [(B,) Lq/q_per_ref, L, 2|4] -> bf16 [B*Lq, M*D]."""
+    _cuda(value, "value", BF16), _cuda(proj, "proj", torch.float32), _cuda(ref, "ref", torch.float32)
+    _cuda(spatial_shapes, "spatial_shapes", torch.int64), _cuda(level_start_index, "level_start_index", torch.int64)
+    if not (value.is_contiguous() and ref.is_contiguous()):
+        raise TairError("msda_fused: value / ref must be contiguous")
+    p2, ldp = _rows(proj, "proj")
+    _, S, M, D = value.shape
+    ref_dim = ref.shape[-1]
+    n_ref = Lq // q_per_ref
+    if M != n_heads or p2.shape[0] != B * Lq or ref.numel() != (1 if ref_shared else B) * n_ref * n_levels * ref_dim:
+        raise TairError("msda_fused: inconsistent shapes")
+    out = torch.empty((B * Lq, M * D), device=value.device, dtype=BF16)
+    stride = 0 if ref_shared else n_ref * n_levels * ref_dim
+    with _timed("msda", 2.0 * out.numel() + 2.0 * value.numel() + 4.0 * p2.shape[0] * M * n_levels * n_points * 3):
+        rc = _lib.lib().tair_msda_fused(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                        p2.data_ptr(), ldp, ref.data_ptr(), ref_dim, stride, q_per_ref, out.data_ptr(),
+                                        B, S, M, D, n_levels, Lq, n_points, _stream())
+    _lib.check(rc, "tair_msda_fused")
+    return out
+
+
+def mha_small(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_inner: int, outer_stride: int,
+              inner_stride: int, tok_stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv bf16 [rows, 3*E] fused in_proj output; returns the attention output [rows, E] in the same row order."""
+    _cuda(qkv, "qkv", BF16)
+    q2, ld = _rows(qkv, "qkv")
+    E = q2.shape[1] // 3
+    hd = E // n_heads
+    if out is None:
+        out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
+    o2, ldo = _rows(out, "out")
+    rc = _lib.lib().tair_mha_small(q2.data_ptr(), ld, o2.data_ptr(), ldo, n_heads, hd, L, n_outer, n_inner, outer_stride,
+                                   inner_stride, tok_stride, float(hd ** -0.5), _stream())
+    _lib.check(rc, "tair_mha_small")
     return out

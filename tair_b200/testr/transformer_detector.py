@@ -1,0 +1,69 @@
+"""TransformerDetector — the text-spotting entry point called once per denoising step
+(testr/adet/modeling/transformer_detector.py:40-152).  ``forward(extracted_feats, targets, MODE)`` keeps the
+reference contract and returns ``(loss_dict | None, list[Instances])``; only MODE == 'VAL' is on the inference path
+(the training criterion / matcher are out of scope)."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .models import TESTR
+from .structures import Instances
+
+
+def default_cfg(device: str = "cuda") -> SimpleNamespace:
+    """The cfg keys TESTR reads: testr/adet/config/defaults.py:340-369 + testr/configs/TESTR/TESTR_R_50_Polygon.yaml."""
+    tr = SimpleNamespace(ENABLED=True, INFERENCE_TH_TEST=0.5, VOC_SIZE=96, NUM_CHARS=25, AUX_LOSS=True, ENC_LAYERS=6,
+                         DEC_LAYERS=6, DIM_FEEDFORWARD=1024, HIDDEN_DIM=256, DROPOUT=0.1, NHEADS=8, NUM_QUERIES=100,
+                         ENC_N_POINTS=4, DEC_N_POINTS=4, POSITION_EMBEDDING_SCALE=6.283185307179586,
+                         NUM_FEATURE_LEVELS=4, USE_POLYGON=True, NUM_CTRL_POINTS=16)
+    return SimpleNamespace(MODEL=SimpleNamespace(DEVICE=device, TRANSFORMER=tr))
+
+
+class TransformerDetector(nn.Module):
+    def __init__(self, cfg=None):
+        super().__init__()
+        cfg = cfg or default_cfg()
+        self.device = torch.device(cfg.MODEL.DEVICE)
+        self.test_score_threshold = cfg.MODEL.TRANSFORMER.INFERENCE_TH_TEST
+        self.use_polygon = cfg.MODEL.TRANSFORMER.USE_POLYGON
+        self.testr = TESTR(cfg)
+
+    @torch.no_grad()
+    def forward(self, extracted_feats: Sequence[torch.Tensor], targets=None, MODE: str = "VAL"):
+        if MODE != "VAL":
+            raise NotImplementedError("tair_b200 covers the inference path (MODE='VAL'); training losses are out of scope")
+        output = self.testr(extracted_feats)
+        bs = output["pred_logits"].shape[0]
+        image_sizes = [(512, 512) for _ in range(bs)]
+        results = self.inference(output["pred_logits"], output["pred_ctrl_points"], output["pred_texts"], image_sizes)
+        return None, results
+
+    def inference(self, ctrl_point_cls, ctrl_point_coord, text_pred, image_sizes) -> List[Instances]:
+        """transformer_detector.py:123-152: softmax over the vocabulary, score = sigmoid(mean point logit),
+        threshold, scale control points to pixels, arg-max characters."""
+        assert len(ctrl_point_cls) == len(image_sizes)
+        text_pred = torch.softmax(text_pred, dim=-1)
+        prob = ctrl_point_cls.mean(-2).sigmoid()
+        scores, labels = prob.max(-1)
+        results = []
+        for s, lab, pts, txt, size in zip(scores, labels, ctrl_point_coord, text_pred, image_sizes):
+            keep = s >= self.test_score_threshold
+            pts = pts[keep].clone()
+            pts[..., 0] *= size[1]
+            pts[..., 1] *= size[0]
+            txt = txt[keep]
+            r = Instances(size)
+            r.scores = s[keep]
+            r.pred_classes = lab[keep]
+            r.rec_scores = txt
+            if self.use_polygon:
+                r.polygons = pts.flatten(1)
+            else:
+                r.beziers = pts.flatten(1)
+            r.recs = txt.topk(1)[1].squeeze(-1)
+            results.append(r)
+        return results

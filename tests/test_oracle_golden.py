@@ -97,3 +97,21 @@ def test_split_pads_with_zeros_and_orders_row_major():
     assert np.array_equal(ps[0], img[:128, :128])
     assert np.array_equal(ps[1][:, :, 0], img[:128, 112:240, 0])
     assert ps[5][18:, :, :].sum() == 0  # rows below the image are zero padding
+
+
+def test_testr_head_matches_reference_fixture(golden, manifests):
+    from oracle import testr as OT
+    g = golden("testr_full.npz")
+    sd = weights.seeded_state_dict(manifests["testr"])
+    feats = [weights.seeded_randn(s, i) for s, i in (((1, 1280, 16, 16), 41), ((1, 1280, 32, 32), 42),
+                                                      ((1, 640, 64, 64), 43), ((1, 320, 64, 64), 44))]
+    with torch.no_grad():
+        out = OT.testr_forward(sd, feats)
+    assert np.abs(out["pred_logits"].numpy() - g["pred_logits"]).max() < 1e-4
+    assert np.abs(out["pred_ctrl_points"].numpy() - g["pred_ctrl_points"]).max() < 1e-4
+    assert np.abs(out["pred_texts"].numpy() - g["pred_texts"]).max() < 1e-4
+    assert np.abs(out["enc_logits"].numpy()[:, ::8] - g["enc_logits"]).max() < 1e-4
+    r = OT.inference(out)[0]
+    assert len(r["scores"]) == int(g["n_inst"]) > 0
+    assert np.array_equal(r["recs"].numpy(), g["recs"])
+    assert np.abs(r["polygons"].numpy() - g["polygons"]).max() < 1e-2
