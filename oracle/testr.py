@@ -114,7 +114,7 @@ def _branch(sd, p, sfx, tgt, qpos, boxes, memory, shapes, core):
     return _ln(sd, f"{p}.norm3{sfx}", tgt + t2)
 
 
-def testr_forward(sd: SD, feats: Sequence[torch.Tensor], core=msda_core) -> Dict[str, torch.Tensor]:
+def testr_forward(sd: SD, feats: Sequence[torch.Tensor], core=msda_core, proposal_indices=None) -> Dict[str, torch.Tensor]:
     """feats: 4 decoder feature maps (B,C,H,W) fp32 -> pred_logits (B,100,16,1), pred_ctrl_points (B,100,16,2),
     pred_texts (B,100,25,97) of the LAST decoder layer (what inference consumes), plus encoder proposals."""
     sd = canonical(sd)
@@ -161,7 +161,7 @@ def testr_forward(sd: SD, feats: Sequence[torch.Tensor], core=msda_core) -> Dict
     out_mem = _ln(sd, T + ".enc_output_norm", _lin(sd, T + ".enc_output", mem.masked_fill(~valid, 0.0)))
     enc_class = _lin(sd, T + ".bbox_class_embed", out_mem)
     enc_coord = _mlp(sd, T + ".bbox_embed", out_mem) + props_logit
-    top = torch.topk(enc_class[..., 0], N_PROPOSALS, dim=1)[1]
+    top = torch.topk(enc_class[..., 0], N_PROPOSALS, dim=1)[1] if proposal_indices is None else proposal_indices
     top_coord = torch.gather(enc_coord, 1, top[..., None].expand(-1, -1, 4))
     boxes = top_coord.sigmoid()                                     # (B,100,4) reference boxes
     # proposal positional embedding (:66-79) -> query_pos
@@ -189,7 +189,7 @@ def testr_forward(sd: SD, feats: Sequence[torch.Tensor], core=msda_core) -> Dict
     coords = (_mlp(sd, "testr.ctrl_point_coord.5", tgt) + ref_logit[:, :, None, :2]).sigmoid()
     texts = _lin(sd, "testr.text_class", tgt_text)
     return dict(pred_logits=logits, pred_ctrl_points=coords, pred_texts=texts, enc_logits=enc_class,
-                enc_boxes=enc_coord.sigmoid(), boxes=boxes)
+                enc_boxes=enc_coord.sigmoid(), boxes=boxes, topk_indices=top)
 
 
 def inference(out: Dict[str, torch.Tensor], threshold: float = 0.5, image_size=(512, 512)) -> List[Dict[str, torch.Tensor]]:

@@ -157,8 +157,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld_32x32(tm_S + lane_off + cc, sv);
         tmem_ld_wait();
         if (kvalid >= cc + 32) {
+          // four independent chains: a single serial fmax chain is latency-bound with 2 warps per scheduler
+          float m0 = mx, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(sv[i]));
+            m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -180,12 +188,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) o[half * 32 + i] += __uint_as_float(ov[i]);
         }
       }
-      const float alpha = exp2f(m_run - m_new);
+      const float alpha = ex2_approx(m_run - m_new);
 #pragma unroll
       for (int i = 0; i < AT_D; ++i) o[i] *= alpha;
       l_run *= alpha;
       // pass 2: P = exp2(S*c - m_new) -> bf16 -> swizzled smem ; row sum
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < AT_BN; cc += 32) {
         uint32_t sv[32];
@@ -194,11 +202,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = exp2f(fmaf(__uint_as_float(sv[i]), c, -m_new));
+          float e = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -m_new));
           if (cc + i >= kvalid) e = 0.f;
           pv[i] = e;
-          lsum += e;
         }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3]; }
         // 32 columns = 4 chunks of 16 B; chunk index inside the 64-wide k-atom is XOR-swizzled by row
         uint8_t* atom = prow + (cc >> 6) * TILE_BYTES;
         const int chunk0 = (cc & 63) >> 3;
@@ -212,7 +221,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) = w;
         }
       }
-      l_run += lsum;
+      l_run += (ls0 + ls1) + (ls2 + ls3);
       m_run = m_new;
       fence_async_smem();
       tc_fence_before();

@@ -243,6 +243,12 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// single MUFU.EX2 (exp2f without -use_fast_math adds range-fixup instructions)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 // exact (erf) GELU, matching torch.nn.functional.gelu default
 __device__ __forceinline__ float gelu_f(float x) {

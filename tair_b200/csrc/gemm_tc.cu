@@ -31,6 +31,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 256;
 constexpr uint32_t A_BYTES = BM * BK * 2;
+// epilogue staging: each epilogue warp owns 32 rows x 64 bf16 columns, rows padded by 16 B so that both the
+// thread-per-row writes and the row-contiguous reads are bank-conflict free
+constexpr int STG_COLS = 64;
+constexpr int STG_PITCH = STG_COLS * 2 + 16;
+constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH;
+constexpr uint32_t STG_BYTES = 4 * STG_BYTES_PER_WARP;
 
 struct GemmParams {
   int M, N, K;
@@ -46,9 +52,9 @@ template <int BN>
 struct Cfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 160) ? 6 : ((BN >= 128) ? 6 : 8));
+  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 160) ? 5 : ((BN >= 128) ? 6 : 8));
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 };
 
 template <int ACT>
@@ -182,6 +188,127 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
       }
 }
 
+// Staged epilogue (bf16 output): TMEM -> registers (thread = row) -> bias / row add / activation -> bf16 ->
+// padded smem -> each warp re-reads its 32 rows row-contiguously, adds the residual with coalesced 16-byte loads and
+// writes coalesced 16-byte stores.  The direct thread-per-row stores of the first version issued 32 separate
+// half-sector L2 writes per instruction and bounded every small-K GEMM (ncu, profiles/round1_ncu_summary.md).
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_tile_staged(const GemmParams& p, int m0w, int tn, int lane, uint32_t taddr,
+                                                     uint8_t* stg, uint32_t tempty_bar_addr) {
+  const tair_epilogue& e = p.epi;
+  constexpr bool GEGLU = (ACT == TAIR_ACT_GEGLU);
+  constexpr int NT = GEGLU ? BN / 2 : BN;            // output columns produced by this tile
+  const int n_total = GEGLU ? p.N / 2 : p.N;         // output columns of the whole problem
+  const int n_out0 = tn * NT;
+  const int m = m0w + lane;
+  const bool row_ok = m < p.M;
+  const float* rg = nullptr;
+  if (!GEGLU && e.rowgroup != nullptr && row_ok)
+    rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
+  uint8_t* my_row = stg + lane * STG_PITCH;
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
+  const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += STG_COLS) {
+    const int ncol = (NT - c0) < STG_COLS ? (NT - c0) : STG_COLS;
+    // ---- phase A: this thread's row, columns [c0, c0+ncol) ----
+#pragma unroll 1
+    for (int g = 0; g < ncol; g += 32) {
+      uint32_t r[32];
+      float v[32];
+      if constexpr (GEGLU) {
+        uint32_t rgt[32];
+        tmem_ld_32x32(taddr + c0 + g, r);
+        tmem_ld_32x32(taddr + NT + c0 + g, rgt);
+        tmem_ld_wait();
+        const int nv = tn * BN + c0 + g, ng = nv + NT;   // rows of the tile-interleaved weight
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(r[j]), gt = __uint_as_float(rgt[j]);
+          if (e.bias != nullptr) { a += __ldg(e.bias + nv + j); gt += __ldg(e.bias + ng + j); }
+          v[j] = a * gelu_f(gt);
+        }
+      } else {
+        tmem_ld_32x32(taddr + c0 + g, r);
+        tmem_ld_wait();
+        const int n = n_out0 + c0 + g;
+        if (n + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(r[j]);
+            if (e.bias != nullptr) a += __ldg(e.bias + n + j);
+            if (rg != nullptr) a += __ldg(rg + n + j);
+            v[j] = apply_act<ACT>(a);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(r[j]);
+            if (n + j < p.N) {
+              if (e.bias != nullptr) a += __ldg(e.bias + n + j);
+              if (rg != nullptr) a += __ldg(rg + n + j);
+            }
+            v[j] = apply_act<ACT>(a);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 w;
+        w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(my_row + (g + q * 8) * 2) = w;
+      }
+    }
+    if (c0 + STG_COLS >= NT) {  // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar_addr);
+    } else {
+      __syncwarp();
+    }
+    // ---- phase B: the warp's 32 rows, row-contiguous 16-byte chunks ----
+    const int cpr = ncol >> 3;  // 16-byte chunks per row (8 or 4)
+    for (int idx = lane; idx < 32 * cpr; idx += 32) {
+      const int row = idx / cpr, ch = idx - row * cpr;
+      const int mm = m0w + row;
+      const int n = n_out0 + c0 + ch * 8;
+      if (mm < p.M && n < n_total) {
+        uint4 w = *reinterpret_cast<const uint4*>(stg + row * STG_PITCH + ch * 16);
+        if (n + 8 <= n_total) {
+          if (resp != nullptr) {
+            float2 a0 = unpack_bf16(w.x), a1 = unpack_bf16(w.y), a2 = unpack_bf16(w.z), a3 = unpack_bf16(w.w);
+            const __nv_bfloat16* rp = resp + (int64_t)mm * e.ldr + n;
+            if (p.vec_res) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp));
+              float2 b0 = unpack_bf16(q.x), b1 = unpack_bf16(q.y), b2 = unpack_bf16(q.z), b3 = unpack_bf16(q.w);
+              w.x = pack_bf16(a0.x + b0.x, a0.y + b0.y); w.y = pack_bf16(a1.x + b1.x, a1.y + b1.y);
+              w.z = pack_bf16(a2.x + b2.x, a2.y + b2.y); w.w = pack_bf16(a3.x + b3.x, a3.y + b3.y);
+            } else {
+              w.x = pack_bf16(a0.x + __bfloat162float(rp[0]), a0.y + __bfloat162float(rp[1]));
+              w.y = pack_bf16(a1.x + __bfloat162float(rp[2]), a1.y + __bfloat162float(rp[3]));
+              w.z = pack_bf16(a2.x + __bfloat162float(rp[4]), a2.y + __bfloat162float(rp[5]));
+              w.w = pack_bf16(a3.x + __bfloat162float(rp[6]), a3.y + __bfloat162float(rp[7]));
+            }
+          }
+          *reinterpret_cast<uint4*>(outp + (int64_t)mm * e.ldc + n) = w;
+        } else {  // ragged last chunk of the row
+          const __nv_bfloat16* sv = reinterpret_cast<const __nv_bfloat16*>(&w);
+          for (int j = 0; j < 8 && n + j < n_total; ++j) {
+            float f = __bfloat162float(sv[j]);
+            if (resp != nullptr) f += __bfloat162float(resp[(int64_t)mm * e.ldr + n + j]);
+            outp[(int64_t)mm * e.ldc + n + j] = __float2bfloat16(f);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -192,6 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES + 256;
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
@@ -310,16 +438,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
-      switch (e.act) {
-        case TAIR_ACT_GEGLU: epilogue_tile<BN, TAIR_ACT_GEGLU>(p, m, tn, row_ok, taddr); break;
-        case TAIR_ACT_GELU: epilogue_tile<BN, TAIR_ACT_GELU>(p, m, tn, row_ok, taddr); break;
-        case TAIR_ACT_SILU: epilogue_tile<BN, TAIR_ACT_SILU>(p, m, tn, row_ok, taddr); break;
-        case TAIR_ACT_RELU: epilogue_tile<BN, TAIR_ACT_RELU>(p, m, tn, row_ok, taddr); break;
-        default: epilogue_tile<BN, TAIR_ACT_NONE>(p, m, tn, row_ok, taddr); break;
+      if (!e.out_fp32 && p.vec_out) {
+        uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
+        const int m0w = tm * BM + ew * 32;
+        switch (e.act) {
+          case TAIR_ACT_GEGLU: epilogue_tile_staged<BN, TAIR_ACT_GEGLU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_GELU: epilogue_tile_staged<BN, TAIR_ACT_GELU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_SILU: epilogue_tile_staged<BN, TAIR_ACT_SILU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_RELU: epilogue_tile_staged<BN, TAIR_ACT_RELU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
+          default: epilogue_tile_staged<BN, TAIR_ACT_NONE>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
+        }
+      } else {
+        // fp32 / unaligned outputs (small heads): direct thread-per-row stores
+        switch (e.act) {
+          case TAIR_ACT_GEGLU: epilogue_tile<BN, TAIR_ACT_GEGLU>(p, m, tn, row_ok, taddr); break;
+          case TAIR_ACT_GELU: epilogue_tile<BN, TAIR_ACT_GELU>(p, m, tn, row_ok, taddr); break;
+          case TAIR_ACT_SILU: epilogue_tile<BN, TAIR_ACT_SILU>(p, m, tn, row_ok, taddr); break;
+          case TAIR_ACT_RELU: epilogue_tile<BN, TAIR_ACT_RELU>(p, m, tn, row_ok, taddr); break;
+          default: epilogue_tile<BN, TAIR_ACT_NONE>(p, m, tn, row_ok, taddr); break;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

@@ -341,8 +341,10 @@ class TESTR(nn.Module):
 
     # ---- forward ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, samples: Sequence[torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """samples: the 4 UNet decoder feature maps, (B,C,H,W) fp32 (reference convention) or channels-last bf16."""
+    def forward(self, samples: Sequence[torch.Tensor], proposal_indices: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """samples: the 4 UNet decoder feature maps, (B,C,H,W) fp32 (reference convention) or channels-last bf16.
+        ``proposal_indices`` (B,100) overrides the top-k proposal selection (teacher forcing for parity tests: the
+        hard top-k makes everything downstream discontinuous in the encoder logits)."""
         feats = [f if f.dtype == BF16 else ops.nchw_to_nhwc(f.float()) for f in samples]
         B, dev, d = feats[0].shape[0], feats[0].device, self.d_model
         srcs, shapes = [], []
@@ -362,7 +364,7 @@ class TESTR(nn.Module):
         masked = (mem.view(B, S, d) * c["valid"]).view(B * S, d)
         out_mem = T.enc_output_norm(T.enc_output(masked))
         enc_class = self.bbox_class(out_mem, out_dtype=F32).view(B, S)
-        top = torch.topk(enc_class, self.num_proposals, dim=1)[1]                                        # [B,100]
+        top = torch.topk(enc_class, self.num_proposals, dim=1)[1] if proposal_indices is None else proposal_indices
         sel = torch.gather(out_mem.view(B, S, d), 1, top[..., None].expand(-1, -1, d)).reshape(-1, d)
         coord_unact = self.bbox_coord(sel.contiguous()).view(B, -1, 4) + c["props_logit"][top]
         boxes = coord_unact.sigmoid()                                                                    # [B,100,4]
@@ -390,4 +392,5 @@ class TESTR(nn.Module):
         coords = (self.ctrl_point_coord[last](tgt).view(B, n_obj, n_pt, 2) + ref_logit[:, :, None, :2]).sigmoid()
         texts = self.text_class(tgt_text, out_dtype=F32).view(B, n_obj, n_ch, self.voc_size + 1)
         return {"pred_logits": logits, "pred_ctrl_points": coords, "pred_texts": texts,
-                "enc_outputs": {"pred_logits": enc_class[..., None], "pred_boxes": None, "pred_filtered_boxes": boxes}}
+                "enc_outputs": {"pred_logits": enc_class[..., None], "pred_boxes": None, "pred_filtered_boxes": boxes,
+                                "topk_indices": top}}
