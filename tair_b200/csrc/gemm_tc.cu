@@ -17,6 +17,7 @@
 // activation with shifted (w,h) start coordinates; TMA's out-of-bounds zero fill implements
 // the padding and elementStrides implements stride 2.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/tair_b200.h"
 #include "common.cuh"
@@ -29,14 +30,13 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4..11 epilogue
 constexpr uint32_t A_BYTES = BM * BK * 2;
-// epilogue staging: each epilogue warp owns 32 rows x 64 bf16 columns, rows padded by 16 B so that both the
-// thread-per-row writes and the row-contiguous reads are bank-conflict free
-constexpr int STG_COLS = 64;
-constexpr int STG_PITCH = STG_COLS * 2 + 16;
-constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH;
-constexpr uint32_t STG_BYTES = 4 * STG_BYTES_PER_WARP;
+// epilogue staging: each of the 8 epilogue warps owns one 32-row x 64-column bf16 sub-tile (4 KB) written in the
+// 128B-swizzled layout of a TMA store box, so the global write is one cp.async.bulk.tensor per sub-tile
+constexpr int EPI_WARPS = 8;
+constexpr uint32_t STG_BYTES_PER_WARP = 32 * 128;
+constexpr uint32_t STG_BYTES = EPI_WARPS * STG_BYTES_PER_WARP;
 
 struct GemmParams {
   int M, N, K;
@@ -45,6 +45,8 @@ struct GemmParams {
   int kb_per_tap;  // Cin / 64
   int Ho, Wo, stride;
   int vec_out, vec_res;
+  int tma_store;  // bf16 output eligible for the TMA-store epilogue
+  int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the whole epilogue body, 4 load B once
   tair_epilogue epi;
 };
 
@@ -188,51 +190,67 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
       }
 }
 
-// Staged epilogue (bf16 output): TMEM -> registers (thread = row) -> bias / row add / activation -> bf16 ->
-// padded smem -> each warp re-reads its 32 rows row-contiguously, adds the residual with coalesced 16-byte loads and
-// writes coalesced 16-byte stores.  The direct thread-per-row stores of the first version issued 32 separate
-// half-sector L2 writes per instruction and bounded every small-K GEMM (ncu, profiles/round1_ncu_summary.md).
+// TMA-store epilogue (bf16 output).  Eight warps: warp e drains TMEM lane quadrant (e & 3) for the 64-column
+// sub-tiles s with (s & 1) == (e >> 2).  Per sub-tile: tcgen05.ld (thread = output row) -> bias / row add /
+// activation / residual -> bf16 -> swizzled smem -> one cp.async.bulk.tensor store (rows >= M and columns >= N are
+// clipped by the hardware).  History: direct thread-per-row stores and a smem row-copy variant were both bound by
+// the single epilogue warp per scheduler executing ~1000 dependent address/LSU instructions per tile (ncu source
+// page, profiles/round1_summary.md); the bulk store removes that code entirely.
 template <int BN, int ACT>
-__device__ __forceinline__ void epilogue_tile_staged(const GemmParams& p, int m0w, int tn, int lane, uint32_t taddr,
-                                                     uint8_t* stg, uint32_t tempty_bar_addr) {
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC64,
+                                                  const CUtensorMap* tmC32, int m0q, int tn, int half, int lane,
+                                                  uint32_t taddr, uint8_t* stg, uint32_t tempty_bar_addr) {
   const tair_epilogue& e = p.epi;
   constexpr bool GEGLU = (ACT == TAIR_ACT_GEGLU);
-  constexpr int NT = GEGLU ? BN / 2 : BN;            // output columns produced by this tile
-  const int n_total = GEGLU ? p.N / 2 : p.N;         // output columns of the whole problem
+  constexpr int NT = GEGLU ? BN / 2 : BN;      // output columns produced by this tile
+  constexpr int NSUB = (NT + 63) / 64;
+  const int n_total = GEGLU ? p.N / 2 : p.N;
   const int n_out0 = tn * NT;
-  const int m = m0w + lane;
+  const int m = m0q + lane;
   const bool row_ok = m < p.M;
   const float* rg = nullptr;
   if (!GEGLU && e.rowgroup != nullptr && row_ok)
     rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
-  uint8_t* my_row = stg + lane * STG_PITCH;
-  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
-  const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+  const __nv_bfloat16* resp = (e.residual != nullptr && row_ok)
+                                  ? reinterpret_cast<const __nv_bfloat16*>(e.residual) + (int64_t)m * e.ldr : nullptr;
+  const uint32_t stg_u32 = smem_u32(stg);
+  const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
 
+  if (half >= NSUB) {  // nothing to drain for this warp (narrow tiles): just release the accumulator
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar_addr);
+    return;
+  }
 #pragma unroll 1
-  for (int c0 = 0; c0 < NT; c0 += STG_COLS) {
-    const int ncol = (NT - c0) < STG_COLS ? (NT - c0) : STG_COLS;
-    // ---- phase A: this thread's row, columns [c0, c0+ncol) ----
+  for (int s = half; s < NSUB; s += 2) {
+    const int c0 = s * 64;
+    const int ncol = (NT - c0) < 64 ? (NT - c0) : 64;  // 64, or 32 for the tail of BN = 160
+    if (lane == 0) tma_store_wait_read<0>();           // previous store of this warp has left the staging buffer
+    __syncwarp();
 #pragma unroll 1
     for (int g = 0; g < ncol; g += 32) {
-      uint32_t r[32];
       float v[32];
+      const int n = n_out0 + c0 + g;                   // first output column of this 32-wide group
       if constexpr (GEGLU) {
-        uint32_t rgt[32];
-        tmem_ld_32x32(taddr + c0 + g, r);
-        tmem_ld_32x32(taddr + NT + c0 + g, rgt);
-        tmem_ld_wait();
-        const int nv = tn * BN + c0 + g, ng = nv + NT;   // rows of the tile-interleaved weight
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(r[j]), gt = __uint_as_float(rgt[j]);
-          if (e.bias != nullptr) { a += __ldg(e.bias + nv + j); gt += __ldg(e.bias + ng + j); }
-          v[j] = a * gelu_f(gt);
+        for (int h2 = 0; h2 < 2; ++h2) {               // 16 columns at a time keeps register pressure down
+          uint32_t rv[16], rgt[16];
+          tmem_ld_32x16(taddr + c0 + g + h2 * 16, rv);
+          tmem_ld_32x16(taddr + NT + c0 + g + h2 * 16, rgt);
+          tmem_ld_wait();
+          const int nv = tn * BN + c0 + g + h2 * 16, ng = nv + NT;   // rows of the tile-interleaved weight
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(rv[j]), gt = __uint_as_float(rgt[j]);
+            if (e.bias != nullptr) { a += __ldg(e.bias + nv + j); gt += __ldg(e.bias + ng + j); }
+            v[h2 * 16 + j] = a * gelu_f(gt);
+          }
         }
       } else {
+        uint32_t r[32];
         tmem_ld_32x32(taddr + c0 + g, r);
         tmem_ld_wait();
-        const int n = n_out0 + c0 + g;
         if (n + 32 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -253,6 +271,21 @@ __device__ __forceinline__ void epilogue_tile_staged(const GemmParams& p, int m0
           }
         }
       }
+      if (resp != nullptr) {
+        if (p.vec_res && n + 32 <= n_total) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(resp + n + q * 8));
+            const float2 b0 = unpack_bf16(w.x), b1 = unpack_bf16(w.y), b2 = unpack_bf16(w.z), b3 = unpack_bf16(w.w);
+            v[q * 8 + 0] += b0.x; v[q * 8 + 1] += b0.y; v[q * 8 + 2] += b1.x; v[q * 8 + 3] += b1.y;
+            v[q * 8 + 4] += b2.x; v[q * 8 + 5] += b2.y; v[q * 8 + 6] += b3.x; v[q * 8 + 7] += b3.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n + j < n_total) v[j] += __bfloat162float(resp[n + j]);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 w;
@@ -260,66 +293,38 @@ __device__ __forceinline__ void epilogue_tile_staged(const GemmParams& p, int m0
         w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
         w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
         w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-        *reinterpret_cast<uint4*>(my_row + (g + q * 8) * 2) = w;
+        // swizzled position of 16-byte chunk (g/8 + q) of this row inside the TMA box
+        uint8_t* dst = (ncol == 64) ? stg + lane * 128 + ((((g >> 3) + q) ^ sw7) << 4)
+                                    : stg + lane * 64 + ((q ^ sw3) << 4);
+        *reinterpret_cast<uint4*>(dst) = w;
       }
     }
-    if (c0 + STG_COLS >= NT) {  // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar_addr);
-    } else {
-      __syncwarp();
-    }
-    // ---- phase B: the warp's 32 rows, row-contiguous 16-byte chunks ----
-    const int cpr = ncol >> 3;  // 16-byte chunks per row (8 or 4)
-    for (int idx = lane; idx < 32 * cpr; idx += 32) {
-      const int row = idx / cpr, ch = idx - row * cpr;
-      const int mm = m0w + row;
-      const int n = n_out0 + c0 + ch * 8;
-      if (mm < p.M && n < n_total) {
-        uint4 w = *reinterpret_cast<const uint4*>(stg + row * STG_PITCH + ch * 16);
-        if (n + 8 <= n_total) {
-          if (resp != nullptr) {
-            float2 a0 = unpack_bf16(w.x), a1 = unpack_bf16(w.y), a2 = unpack_bf16(w.z), a3 = unpack_bf16(w.w);
-            const __nv_bfloat16* rp = resp + (int64_t)mm * e.ldr + n;
-            if (p.vec_res) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp));
-              float2 b0 = unpack_bf16(q.x), b1 = unpack_bf16(q.y), b2 = unpack_bf16(q.z), b3 = unpack_bf16(q.w);
-              w.x = pack_bf16(a0.x + b0.x, a0.y + b0.y); w.y = pack_bf16(a1.x + b1.x, a1.y + b1.y);
-              w.z = pack_bf16(a2.x + b2.x, a2.y + b2.y); w.w = pack_bf16(a3.x + b3.x, a3.y + b3.y);
-            } else {
-              w.x = pack_bf16(a0.x + __bfloat162float(rp[0]), a0.y + __bfloat162float(rp[1]));
-              w.y = pack_bf16(a1.x + __bfloat162float(rp[2]), a1.y + __bfloat162float(rp[3]));
-              w.z = pack_bf16(a2.x + __bfloat162float(rp[4]), a2.y + __bfloat162float(rp[5]));
-              w.w = pack_bf16(a3.x + __bfloat162float(rp[6]), a3.y + __bfloat162float(rp[7]));
-            }
-          }
-          *reinterpret_cast<uint4*>(outp + (int64_t)mm * e.ldc + n) = w;
-        } else {  // ragged last chunk of the row
-          const __nv_bfloat16* sv = reinterpret_cast<const __nv_bfloat16*>(&w);
-          for (int j = 0; j < 8 && n + j < n_total; ++j) {
-            float f = __bfloat162float(sv[j]);
-            if (resp != nullptr) f += __bfloat162float(resp[(int64_t)mm * e.ldr + n + j]);
-            outp[(int64_t)mm * e.ldc + n + j] = __float2bfloat16(f);
-          }
-        }
-      }
-    }
+    const bool last = (s + 2 >= NSUB);
+    if (last) tc_fence_before();   // all TMEM reads of this tile by this warp are done
+    fence_async_smem();            // staging writes -> visible to the TMA (async proxy)
     __syncwarp();
+    if (lane == 0) {
+      if (last) mbar_arrive(tempty_bar_addr);
+      if (!(p.dbg & 1)) {
+        tma_store_2d(ncol == 64 ? tmC64 : tmC32, stg_u32, n_out0 + c0, m0q);
+        tma_store_commit();
+      }
+    }
   }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC64, const __grid_constant__ CUtensorMap tmC32,
                const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES + 256;
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
@@ -338,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -372,7 +377,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const bool skip_b = (p.dbg & 4) && tile != (int)blockIdx.x;
+          mbar_expect_tx(full_bar(stage), skip_b ? A_BYTES : C::STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           if (!p.conv) {
@@ -383,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_4d(a_dst, &tmA, full_bar(stage), cb * BK, wo0 * p.stride + dx - 1,
                         ho0 * p.stride + dy - 1, img);
           }
-          tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
+          if (!skip_b) tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -428,28 +434,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
+    const int quad = ew & 3;   // TMEM lane quadrant (== warp % 4, the only lanes this warp may read)
+    const int half = ew >> 2;  // which alternate 64-column sub-tiles this warp drains
     const tair_epilogue& e = p.epi;
+    uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      const int m = tm * BM + ew * 32 + lane;
-      const bool row_ok = m < p.M;
+      const int m0q = tm * BM + quad * 32;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
-      if (!e.out_fp32 && p.vec_out) {
-        uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
-        const int m0w = tm * BM + ew * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      if ((p.dbg & 2) || (!p.tma_store && half == 1)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      } else if (p.tma_store) {
         switch (e.act) {
-          case TAIR_ACT_GEGLU: epilogue_tile_staged<BN, TAIR_ACT_GEGLU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
-          case TAIR_ACT_GELU: epilogue_tile_staged<BN, TAIR_ACT_GELU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
-          case TAIR_ACT_SILU: epilogue_tile_staged<BN, TAIR_ACT_SILU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
-          case TAIR_ACT_RELU: epilogue_tile_staged<BN, TAIR_ACT_RELU>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
-          default: epilogue_tile_staged<BN, TAIR_ACT_NONE>(p, m0w, tn, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
+          default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
         }
       } else {
-        // fp32 / unaligned outputs (small heads): direct thread-per-row stores
+        // fp32 / unaligned outputs (small heads): direct thread-per-row stores by the first four epilogue warps
+        const int m = m0q + lane;
+        const bool row_ok = m < p.M;
         switch (e.act) {
           case TAIR_ACT_GEGLU: epilogue_tile<BN, TAIR_ACT_GEGLU>(p, m, tn, row_ok, taddr); break;
           case TAIR_ACT_GELU: epilogue_tile<BN, TAIR_ACT_GELU>(p, m, tn, row_ok, taddr); break;
@@ -464,6 +476,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all<0>();  // bulk stores must have completed before the CTA releases its smem
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -475,7 +489,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
+              const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     TAIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -484,7 +499,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& 
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC64, tmC32, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("gemm_tc_kernel");
 }
@@ -526,11 +541,22 @@ int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, 
   if (rc) return rc;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + bn - 1) / bn;
+  // output maps for the TMA-store epilogue: 32-row x 64-column (128B swizzle) and 32 x 32 (64B swizzle) boxes
+  CUtensorMap tmC64 = tmB, tmC32 = tmB;
+  p.tma_store = (!p.epi.out_fp32 && p.vec_out) ? 1 : 0;
+  if (p.tma_store) {
+    const int n_out = (p.epi.act == TAIR_ACT_GEGLU) ? p.N / 2 : p.N;
+    const uint64_t dimsC[2] = {(uint64_t)n_out, (uint64_t)p.M};
+    const uint64_t strC[1] = {(uint64_t)p.epi.ldc * 2};
+    const uint32_t box64[2] = {64, 32}, box32[2] = {32, 32};
+    if ((rc = make_tmap_bf16(&tmC64, p.epi.out, 2, dimsC, strC, box64, nullptr, 3))) return rc;
+    if ((rc = make_tmap_bf16(&tmC32, p.epi.out, 2, dimsC, strC, box32, nullptr, 2))) return rc;
+  }
   switch (bn) {
-    case 256: return launch_bn<256>(tmA, tmB, p, st);
-    case 160: return launch_bn<160>(tmA, tmB, p, st);
-    case 128: return launch_bn<128>(tmA, tmB, p, st);
-    case 64: return launch_bn<64>(tmA, tmB, p, st);
+    case 256: return launch_bn<256>(tmA, tmB, tmC64, tmC32, p, st);
+    case 160: return launch_bn<160>(tmA, tmB, tmC64, tmC32, p, st);
+    case 128: return launch_bn<128>(tmA, tmB, tmC64, tmC32, p, st);
+    case 64: return launch_bn<64>(tmA, tmB, tmC64, tmC32, p, st);
   }
   set_error("gemm: unsupported BN %d", bn);
   return TAIR_ERR_UNSUPPORTED;
@@ -544,6 +570,10 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   if (e->act == TAIR_ACT_GEGLU)
     TAIR_REQUIRE(e->rowgroup == nullptr, "GEGLU epilogue does not take a row-group add");
   p.epi = *e;
+  {
+    const char* d = getenv("TAIR_GEMM_DEBUG");
+    p.dbg = d ? atoi(d) : 0;
+  }
   const int esz = e->out_fp32 ? 4 : 2;
   p.vec_out = ((reinterpret_cast<uintptr_t>(e->out) % 16) == 0) && ((e->ldc * esz) % 16 == 0);
   p.vec_res = e->residual && ((reinterpret_cast<uintptr_t>(e->residual) % 16) == 0) &&

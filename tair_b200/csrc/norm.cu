@@ -63,7 +63,22 @@ __global__ void gn_stats_kernel(const GnParams p) {
   int r1 = r0 + p.rows_per_slab;
   if (r1 > p.HW) r1 = p.HW;
   const __nv_bfloat16* xb = p.x + (int64_t)b * p.HW * p.C + c0;
-  for (int r = r0 + rsub; r < r1; r += p.rows_per_iter) {
+  // 4 independent 16-byte loads in flight per thread (memory-level parallelism), then a scalar tail
+  int r = r0 + rsub;
+  const int step = p.rows_per_iter;
+  for (; r + 3 * step < r1; r += 4 * step) {
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)(r + u * step) * p.C));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 a = unpack_bf16(q[u].x), b2 = unpack_bf16(q[u].y), c = unpack_bf16(q[u].z), d = unpack_bf16(q[u].w);
+      const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sm[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+    }
+  }
+  for (; r < r1; r += step) {
     float f[8];
     load8(xb + (int64_t)r * p.C, f);
 #pragma unroll
@@ -127,9 +142,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
   int r1 = r0 + p.rows_per_slab;
   if (r1 > p.HW) r1 = p.HW;
   const int64_t base = (int64_t)b * p.HW * p.C + c0;
-  for (int r = r0 + rsub; r < r1; r += p.rows_per_iter) {
-    float f[8];
-    load8(p.x + base + (int64_t)r * p.C, f);
+  auto finish = [&](float (&f)[8], int r) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float v = fmaf(f[i], sc[i], sh[i]);
@@ -138,6 +151,20 @@ __global__ void gn_apply_kernel(const GnParams p) {
       f[i] = v;
     }
     store8(p.y + base + (int64_t)r * p.C, f);
+  };
+  int r = r0 + rsub;
+  const int step = p.rows_per_iter;
+  for (; r + 3 * step < r1; r += 4 * step) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(p.x + base + (int64_t)(r + u * step) * p.C, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) finish(f[u], r + u * step);
+  }
+  for (; r < r1; r += step) {
+    float f[8];
+    load8(p.x + base + (int64_t)r * p.C, f);
+    finish(f, r);
   }
 }
 
