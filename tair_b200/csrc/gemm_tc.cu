@@ -504,14 +504,15 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   return check_launch("gemm_tc_kernel");
 }
 
-// Cycles per K=16 step of one 128xBN tile: the larger of the tensor-pipe floor
-// (128*BN/256) and the shared-memory operand read (A 4 KB + B BN*32 B at 128 B/clk).
+// Cycles per K=16 step of one 128xBN tile: the larger of the tensor-pipe floor (128*BN/256) and the shared-memory
+// operand read (A 4 KB + B BN*32 B at ~115 B/clk sustained).
 int tile_cost(int bn) {
-  int mma = bn / 2, smem = 32 + bn / 4;
+  const int mma = bn / 2, smem = (4096 + bn * 32) / 115;
   return mma > smem ? mma : smem;
 }
 
-int pick_bn(int M, int N, int act) {
+// Pick the N tile that minimises  waves x (mainloop cycles + fixed per-tile overhead).
+int pick_bn(int M, int N, int num_kb, int act) {
   if (act == TAIR_ACT_GEGLU) return (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 0);
   const int cands[4] = {256, 160, 128, 64};
   const int tiles_m = (M + BM - 1) / BM;
@@ -522,7 +523,7 @@ int pick_bn(int M, int N, int act) {
     const int bn = cands[i];
     const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
     const long waves = (tiles + sms - 1) / sms;
-    const long cost = waves * tile_cost(bn);
+    const long cost = waves * ((long)num_kb * (BK / 16) * tile_cost(bn) + 700);
     if (best < 0 || cost < best) {
       best = cost;
       best_bn = bn;
@@ -603,7 +604,7 @@ extern "C" int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   const int n_out = (act == TAIR_ACT_GEGLU) ? N / 2 : N;
   int rc = check_epilogue(epi, p, n_out);
   if (rc) return rc;
-  const int bn = pick_bn(M, N, act);
+  const int bn = pick_bn(M, N, p.num_kb, act);
   TAIR_REQUIRE(bn != 0, "gemm: GEGLU epilogue needs N %% 128 == 0 (N=%d)", N);
   CUtensorMap tmA;
   const uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M};
@@ -644,7 +645,7 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   TAIR_REQUIRE(act != TAIR_ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
   int rc = check_epilogue(epi, p, Cout);
   if (rc) return rc;
-  const int bn = pick_bn(p.M, p.N, act);
+  const int bn = pick_bn(p.M, p.N, p.num_kb, act);
 
   CUtensorMap tmA;
   const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
