@@ -29,7 +29,8 @@ def seeded(shape, seed, scale=1.0):
 
 
 def gen_manifest():
-    out = {}
+    path = os.path.join(HERE, "manifests.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
     for name, kw in (("narrow", NARROW), ("full", {})):
         out[f"unet_{name}"] = Wt.manifest_of(H.build_unet(**kw))
         out[f"controlnet_{name}"] = Wt.manifest_of(H.build_controlnet(**kw))
@@ -133,9 +134,29 @@ def gen_testr():
     print("testr_full: instances", len(r.scores), "logit std", out["pred_logits"].std().item())
 
 
+def gen_vae():
+    H.install()
+    from terediff.model.vae import AutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    vae = AutoencoderKL(dd, 4).eval()
+    man = {k: v for k, v in Wt.manifest_of(vae).items() if k.startswith(("decoder.", "post_quant_conv."))}
+    sd = Wt.seeded_state_dict(man)
+    vae.load_state_dict(sd, strict=False)
+    z = seeded((1, 4, 16, 16), 51)
+    with torch.no_grad():
+        img = vae.decode(z)
+    import json
+    mf = json.load(open(os.path.join(HERE, "manifests.json")))
+    mf["vae_decoder"] = man
+    json.dump(mf, open(os.path.join(HERE, "manifests.json"), "w"))
+    np.savez_compressed(os.path.join(HERE, "vae_decode.npz"), img=img.numpy()[:, :, ::2, ::2])
+    print("vae_decode: img std", img.std().item(), "keys", len(man))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["manifest", "unet", "sched", "msda", "merge", "testr"]
     torch.manual_seed(0)
     for w in what:
         {"manifest": gen_manifest, "unet": gen_unet, "sched": gen_sched, "msda": gen_msda, "merge": gen_merge,
-         "testr": gen_testr}[w]()
+         "testr": gen_testr, "vae": gen_vae}[w]()

@@ -115,3 +115,15 @@ def test_testr_head_matches_reference_fixture(golden, manifests):
     assert len(r["scores"]) == int(g["n_inst"]) > 0
     assert np.array_equal(r["recs"].numpy(), g["recs"])
     assert np.abs(r["polygons"].numpy() - g["polygons"]).max() < 1e-2
+
+
+def test_vae_decoder_matches_reference_fixture(golden, manifests):
+    from oracle import vae
+    g = golden("vae_decode.npz")
+    sd = weights.seeded_state_dict(manifests["vae_decoder"])
+    with torch.no_grad():
+        img = vae.vae_decode(sd, weights.seeded_randn((1, 4, 16, 16), 51))
+    assert img.shape == (1, 3, 128, 128)
+    assert np.abs(img.numpy()[:, :, ::2, ::2] - g["img"]).max() < 1e-3 * max(1.0, np.abs(g["img"]).max())
+    a = torch.rand(2, 3, 8, 8)
+    assert torch.allclose(vae.psnr(a, a), torch.full((2,), 80.0, dtype=torch.float64))
