@@ -6,11 +6,12 @@
 // One CTA = one (batch, head, 128-query tile); two CTAs are co-resident per SM so that one
 // CTA's softmax (CUDA cores / MUFU) overlaps the other's tensor-core work.
 //   warp 0       TMA producer: Q once, then K/V blocks of 128 keys into a 2-stage ring
-//   warp 1       TMEM owner + MMA issuer: S = Q K^T (M128 N128 K64) and O_j = P V (M128 N64 K128)
-//   warps 2..5   softmax: one thread per query row; S read with tcgen05.ld, running max / sum in
-//                registers, P written as bf16 into 128B-swizzled smem (the A operand of P V),
-//                per-block O_j read back from TMEM and accumulated (with rescale) in registers
-// TMEM (256 columns): S fp32 [0,128) | O_j double buffer [128,192) [192,256).
+//   warp 1       TMEM owner + MMA issuer: S = Q K^T (SS, M128 N128 K64) and O += P V (TS: P read from TMEM)
+//   warps 2..5   softmax: one thread per query row; S read with tcgen05.ld; P = exp2(S*c - m) written back as
+//                packed bf16 with tcgen05.st over the S columns it has already consumed
+// O accumulates in TMEM across key blocks; the running maximum is updated lazily (only when a block's maximum
+// exceeds it by more than 2^8, so exp2 arguments stay <= 8), in which case the softmax threads rescale O in TMEM.
+// TMEM (256 columns): S fp32 [0,128) aliased by P bf16x2 [0,64) | O fp32 [128,192).
 #include <atomic>
 #include <math_constants.h>
 
@@ -29,8 +30,7 @@ constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // 16 KB: one 128-row x 64-col bf
 constexpr uint32_t SM_Q = 0;
 constexpr uint32_t SM_K = SM_Q + TILE_BYTES;          // 2 stages
 constexpr uint32_t SM_V = SM_K + 2 * TILE_BYTES;      // 2 stages
-constexpr uint32_t SM_P = SM_V + 2 * TILE_BYTES;      // 2 k-atoms of 16 KB
-constexpr uint32_t SM_BAR = SM_P + 2 * TILE_BYTES;
+constexpr uint32_t SM_BAR = SM_V + 2 * TILE_BYTES;
 constexpr uint32_t AT_SMEM = SM_BAR + 128;
 constexpr uint32_t AT_TMEM_COLS = 256;
 
@@ -53,7 +53,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t p_full = bar + 16;
   auto kv_full = [&](int s) { return bar + 24 + 8u * s; };
   auto kv_empty = [&](int s) { return bar + 40 + 8u * s; };
-  auto o_full = [&](int b) { return bar + 56 + 8u * b; };
+  const uint32_t o_done = bar + 56;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,8 +70,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
-      mbar_init(o_full(s), 1);
     }
+    mbar_init(o_done, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -122,14 +122,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int s = j & 1;
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t pa = sbase + SM_P, va = sbase + SM_V + s * TILE_BYTES;
+        const uint32_t va = sbase + SM_V + s * TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)
-          umma_ss(tm_O + s * 64, umma_desc_sw128(pa + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(va + k * 2048, 16, 1024), idesc_o, k != 0);
-        umma_commit(o_full(s));
+        for (int k = 0; k < AT_BN / 16; ++k)  // A = P from TMEM: 16 bf16 of K per step = 8 columns
+          umma_ts(tm_O, tm_S + k * 8, umma_desc_sw128(va + k * 2048, 16, 1024), idesc_o, (j | k) != 0);
         umma_commit(kv_empty(s));
-        if (j + 1 < p.nblk) issue_s(j + 1);
+        if (j + 1 < p.nblk) issue_s(j + 1);   // its commit (s_full) also covers the P V just issued
+        else umma_commit(o_done);
       }
     }
     __syncwarp();
@@ -137,18 +136,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;       // query row inside the tile
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float o[AT_D];
-#pragma unroll
-    for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
     float m_run = -CUDART_INF_F, l_run = 0.f;
     const float c = p.scale_log2;
-    uint8_t* prow = smem + SM_P + (r >> 3) * 1024 + (r & 7) * 128;
-    const int sw = r & 7;
 
     for (int j = 0; j < p.nblk; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);   // S(j) is complete; in-order tensor pipe => P V(j-1) has retired too
       tc_fence_after();
       const int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
+      const bool full = kvalid >= AT_BN;
       // pass 1: row max
       float mx = -CUDART_INF_F;
 #pragma unroll 1
@@ -156,7 +151,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t sv[32];
         tmem_ld_32x32(tm_S + lane_off + cc, sv);
         tmem_ld_wait();
-        if (kvalid >= cc + 32) {
+        if (full || kvalid >= cc + 32) {
           // four independent chains: a single serial fmax chain is latency-bound with 2 warps per scheduler
           float m0 = mx, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
@@ -173,26 +168,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (cc + i < kvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
         }
       }
-      const float m_new = fmaxf(m_run, mx * c);
-      // fold in the previous block's P V (ready once its MMA retired; also frees the P buffer)
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(o_full(pb), ((j - 1) >> 1) & 1);
-        tc_fence_after();
+      // lazy running maximum: move it only when this block exceeds it by more than 8 (in log2 units)
+      const float m_blk = mx * c;
+      const bool bump = m_blk > m_run + 8.f;
+      if (__any_sync(0xffffffffu, bump)) {
+        const float m_new = bump ? m_blk : m_run;
+        const float alpha = ex2_approx(m_run - m_new);   // 1 for lanes that keep their maximum, 0 on the first block
+        l_run *= alpha;
+        m_run = m_new;
+        if (j > 0) {  // rescale the accumulated O row in TMEM
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t ov[32];
-          tmem_ld_32x32(tm_O + lane_off + pb * 64 + half * 32, ov);
-          tmem_ld_wait();
+          for (int half = 0; half < 4; ++half) {
+            uint32_t ov[16];
+            tmem_ld_32x16(tm_O + lane_off + half * 16, ov);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[half * 32 + i] += __uint_as_float(ov[i]);
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x16(tm_O + lane_off + half * 16, ov);
+          }
         }
       }
-      const float alpha = ex2_approx(m_run - m_new);
-#pragma unroll
-      for (int i = 0; i < AT_D; ++i) o[i] *= alpha;
-      l_run *= alpha;
-      // pass 2: P = exp2(S*c - m_new) -> bf16 -> swizzled smem ; row sum
+      // pass 2: P = exp2(S*c - m) -> packed bf16 -> TMEM columns [cc/2, cc/2+16) (S columns already consumed)
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < AT_BN; cc += 32) {
@@ -200,60 +196,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld_32x32(tm_S + lane_off + cc, sv);
         tmem_ld_wait();
         float pv[32];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -m_new));
-          if (cc + i >= kvalid) e = 0.f;
-          pv[i] = e;
+          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -m_run));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -m_run));
+            pv[i] = (cc + i < kvalid) ? e : 0.f;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3]; }
-        // 32 columns = 4 chunks of 16 B; chunk index inside the 64-wide k-atom is XOR-swizzled by row
-        uint8_t* atom = prow + (cc >> 6) * TILE_BYTES;
-        const int chunk0 = (cc & 63) >> 3;
+        uint32_t pk[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]);
-          w.y = pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]);
-          w.z = pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]);
-          w.w = pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) = w;
-        }
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+        tmem_st_32x16(tm_S + lane_off + (cc >> 1), pk);
       }
       l_run += (ls0 + ls1) + (ls2 + ls3);
-      m_run = m_new;
-      fence_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // last block's P V
-    {
-      const int pb = (p.nblk - 1) & 1;
-      mbar_wait(o_full(pb), ((p.nblk - 1) >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t ov[32];
-        tmem_ld_32x32(tm_O + lane_off + pb * 64 + half * 32, ov);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[half * 32 + i] += __uint_as_float(ov[i]);
-      }
-    }
+    mbar_wait(o_done, 0);
+    tc_fence_after();
     const int q = q0 + r;
-    if (q < p.Lq) {
-      const float inv = 1.f / l_run;
-      __nv_bfloat16* op = p.o + ((int64_t)b * p.Lq + q) * p.ldo + h * AT_D;
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* op = p.o + ((int64_t)b * p.Lq + q) * p.ldo + h * AT_D;
 #pragma unroll
-      for (int i = 0; i < AT_D; i += 8) {
-        uint4 w;
-        w.x = pack_bf16(o[i + 0] * inv, o[i + 1] * inv);
-        w.y = pack_bf16(o[i + 2] * inv, o[i + 3] * inv);
-        w.z = pack_bf16(o[i + 4] * inv, o[i + 5] * inv);
-        w.w = pack_bf16(o[i + 6] * inv, o[i + 7] * inv);
-        *reinterpret_cast<uint4*>(op + i) = w;
+    for (int half = 0; half < 2; ++half) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tm_O + lane_off + half * 32, ov);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(ov[i + 0]) * inv, __uint_as_float(ov[i + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + half * 32 + i) = w;
+        }
       }
     }
   }

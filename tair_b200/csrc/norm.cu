@@ -8,7 +8,7 @@
 //
 // Layout: x is [B, HW, C] (C contiguous).  Every thread owns a fixed 8-channel vector (16 bytes) and
 // walks rows, so loads/stores are 16-byte and fully coalesced; statistics are accumulated in fp32.
-// Pass 1 writes per-slab partial sums (no atomics, deterministic); pass 2 folds them, normalises,
+// Pass 1 writes per-slab partial sums (no atomics anywhere: bit-reproducible); pass 2 folds them, normalises,
 // applies the activation and writes bf16.  Algorithmic traffic: 2 reads + 1 write of the tensor.
 #include <atomic>
 
@@ -45,17 +45,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
-// grid (slabs, B); block = vec_per_row * rows_per_iter threads
+// grid (slabs, B); block = vec_per_row * rows_per_iter threads (<= 320, so <= 2560 channel slots)
 __global__ void gn_stats_kernel(const GnParams p) {
-  __shared__ float s_sum[64], s_sq[64];
+  __shared__ float s_part[2][2560];  // per (row-phase, channel) partial sum / sum of squares
   const int b = blockIdx.y, slab = blockIdx.x;
   const int vec = threadIdx.x % p.vec_per_row;
   const int rsub = threadIdx.x / p.vec_per_row;
   const int c0 = vec * 8;
-  for (int i = threadIdx.x; i < p.G; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
-  __syncthreads();
-  // per-channel partial sums (the thread's 8 channels are fixed across rows), folded per group at the end;
-  // works for any channels-per-group, including groups narrower than one 8-channel vector
+  // per-channel partial sums (the thread's 8 channels are fixed across rows)
   float sm[8], sq[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
@@ -84,27 +81,27 @@ __global__ void gn_stats_kernel(const GnParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sm[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
   }
-  {
-    int g = c0 / p.cpg;
-    float ps = 0.f, pq = 0.f;
+  // deterministic block reduction (no atomics: results must not depend on scheduling, the sampler is a 50-step
+  // recurrence): slot = rsub * C + channel, then one thread per group sums its slots in a fixed order
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int gi = (c0 + i) / p.cpg;
-      if (gi != g) {
-        atomicAdd(&s_sum[g], ps);
-        atomicAdd(&s_sq[g], pq);
-        g = gi; ps = 0.f; pq = 0.f;
-      }
-      ps += sm[i]; pq += sq[i];
-    }
-    atomicAdd(&s_sum[g], ps);
-    atomicAdd(&s_sq[g], pq);
+  for (int i = 0; i < 8; ++i) {
+    s_part[0][rsub * p.C + c0 + i] = sm[i];
+    s_part[1][rsub * p.C + c0 + i] = sq[i];
   }
   __syncthreads();
-  float* w = p.ws + ((int64_t)(b * p.slabs + slab) * p.G) * 2;
-  for (int i = threadIdx.x; i < p.G; i += blockDim.x) {
-    w[2 * i] = s_sum[i];
-    w[2 * i + 1] = s_sq[i];
+  if (threadIdx.x < p.G) {
+    const int g = threadIdx.x;
+    float ps = 0.f, pq = 0.f;
+    for (int rs = 0; rs < p.rows_per_iter; ++rs) {
+      const int base = rs * p.C + g * p.cpg;
+      for (int c = 0; c < p.cpg; ++c) {
+        ps += s_part[0][base + c];
+        pq += s_part[1][base + c];
+      }
+    }
+    float* w = p.ws + ((int64_t)(b * p.slabs + slab) * p.G) * 2;
+    w[2 * g] = ps;
+    w[2 * g + 1] = pq;
   }
 }
 
