@@ -144,29 +144,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       const int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
       const bool full = kvalid >= AT_BN;
-      // pass 1: row max
-      float mx = -CUDART_INF_F;
-#pragma unroll 1
-      for (int cc = 0; cc < AT_BN; cc += 32) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tm_S + lane_off + cc, sv);
-        tmem_ld_wait();
-        if (full || kvalid >= cc + 32) {
-          // four independent chains: a single serial fmax chain is latency-bound with 2 warps per scheduler
-          float m0 = mx, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+      // the whole S row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait, and is
+      // used for both the max and the exponentials (the first version re-read TMEM and stalled on 8 waits per block)
+      uint32_t sv[AT_BN];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+      for (int cc = 0; cc < AT_BN; cc += 32) {
+        uint32_t (&chunk)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[cc]);
+        tmem_ld_32x32(tm_S + lane_off + cc, chunk);
+      }
+      tmem_ld_wait();
+      float mx;
+      {
+        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < AT_BN; i += 4) {
             m0 = fmaxf(m0, __uint_as_float(sv[i]));
             m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
             m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
             m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
           }
-          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc + i < kvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+          for (int i = 0; i < AT_BN; ++i)
+            if (i < kvalid) m0 = fmaxf(m0, __uint_as_float(sv[i]));
         }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       // lazy running maximum: move it only when this block exceeds it by more than 8 (in log2 units)
       const float m_blk = mx * c;
@@ -188,29 +191,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-      // pass 2: P = exp2(S*c - m) -> packed bf16 -> TMEM columns [cc/2, cc/2+16) (S columns already consumed)
+      // P = exp2(S*c - m) -> packed bf16 -> TMEM columns [cc/2, cc/2+16), i.e. over S columns already in registers
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < AT_BN; cc += 32) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tm_S + lane_off + cc, sv);
-        tmem_ld_wait();
-        float pv[32];
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -m_run));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -m_run));
-            pv[i] = (cc + i < kvalid) ? e : 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) { ls0 += pv[i]; ls1 += pv[i + 1]; ls2 += pv[i + 2]; ls3 += pv[i + 3]; }
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+        for (int i = 0; i < 32; i += 4) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 0]), c, -m_run));
+          float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
+          float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
+          float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
+          if (!full) {
+            if (cc + i + 0 >= kvalid) e0 = 0.f;
+            if (cc + i + 1 >= kvalid) e1 = 0.f;
+            if (cc + i + 2 >= kvalid) e2 = 0.f;
+            if (cc + i + 3 >= kvalid) e3 = 0.f;
+          }
+          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+          pk[(i >> 1) + 0] = pack_bf16(e0, e1);
+          pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+        }
         tmem_st_32x16(tm_S + lane_off + (cc >> 1), pk);
       }
       l_run += (ls0 + ls1) + (ls2 + ls3);
