@@ -266,7 +266,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }  // MUFU.RCP, no IEEE divide
 // exact (erf) GELU, matching torch.nn.functional.gelu default
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
