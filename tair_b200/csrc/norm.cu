@@ -168,7 +168,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
 // ---- LayerNorm: a warp normalises LN_ROWS consecutive rows; each lane keeps its gamma/beta slice in registers
 // across rows (re-loading them per row made the kernel instruction-bound: 62 % SM busy at 21 % DRAM in ncu),
 // row values stay in registers for the two-pass mean / variance ----
-constexpr int LN_ROWS = 8;
+constexpr int LN_ROWS = 1;  // >1 trades latency hiding for fewer gamma/beta loads: measured slower on B200 (1.9 vs 1.3 ms per step)
 
 template <int MAXV>  // max 16-byte vectors per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
