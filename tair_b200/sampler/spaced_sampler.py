@@ -175,7 +175,8 @@ class SpacedSampler(Sampler):
 
     @torch.no_grad()
     def val_sample(self, model, device, steps, x_size, cond, uncond, cfg_scale, tiled=False, tile_size=-1,
-                   tile_stride=-1, x_T=None, progress=True, cfg=None, pure_cldm=None, ts_model=None, val_prompt=None):
+                   tile_stride=-1, x_T=None, progress=True, cfg=None, pure_cldm=None, ts_model=None, val_prompt=None,
+                   use_cuda_graph: bool = False):
         """spaced_sampler.py:246-328 -> (x, ts_results): every step runs the text-spotting head on the step's decoder
         features, decodes the recognised strings and re-encodes the prompt that conditions the NEXT step."""
         from ..prompt import build_prompt, decode_texts
@@ -189,13 +190,27 @@ class SpacedSampler(Sampler):
         mode = cfg.exp_args.mode if cfg is not None else "VAL"
         style = cfg.exp_args.prompt_style if cfg is not None else "CAPTION"
         ts_results = []
+        stepper = None
+        if use_cuda_graph and hasattr(ts_model, "testr"):
+            # one graph per step: ControlNet + UNet + sampler update + the dense part of the text-spotting head; only
+            # the data-dependent post-processing (thresholding, string decode, prompt, CLIP) stays outside
+            key = ("val", id(model), id(ts_model), tuple(x.shape), uncond is None)
+            stepper = self._graphs.get(key)
+            if stepper is None:
+                stepper = self._graphs[key] = _StepGraph(self, model, x, cond, uncond, head=ts_model.testr)
         for i, cur in enumerate(order):
             cur = int(cur)
-            model_t = torch.full((bs,), cur, device=device, dtype=torch.long)
-            t = torch.full((bs,), total - i - 1, device=device, dtype=torch.long)
-            x, feats = self.p_sample(model, x, model_t, t, cond, uncond, self.get_cfg_scale(cfg_scale, cur),
-                                     noise=self._noise(i, x))
-            _, results = ts_model(feats, None, mode)
+            scale = self.get_cfg_scale(cfg_scale, cur)
+            if stepper is not None:
+                stepper.load_cond(cond, uncond)
+                x, feats, dense = stepper.run(x, cur, total - i - 1, self._noise(i, x), scale)
+                results = ts_model.inference(dense["pred_logits"], dense["pred_ctrl_points"], dense["pred_texts"],
+                                             [(512, 512)] * bs)
+            else:
+                model_t = torch.full((bs,), cur, device=device, dtype=torch.long)
+                t = torch.full((bs,), total - i - 1, device=device, dtype=torch.long)
+                x, feats = self.p_sample(model, x, model_t, t, cond, uncond, scale, noise=self._noise(i, x))
+                _, results = ts_model(feats, None, mode)
             texts, polys = decode_texts(results)                       # one D2H copy for the whole batch
             prompts = [build_prompt(tx, style) for tx in texts]
             cond["c_txt"] = pure_cldm.clip.encode(prompts if bs > 1 else prompts[0])   # mutated in place like :317
@@ -208,8 +223,8 @@ class _StepGraph:
     """One denoising step (model forward(s) + sampler update) captured in a CUDA graph and replayed per step.
     Static inputs: x, model_t, t, noise, cond tensors; cfg scale is baked per distinct value."""
 
-    def __init__(self, sampler: SpacedSampler, model, x, cond, uncond):
-        self.s, self.model = sampler, model
+    def __init__(self, sampler: SpacedSampler, model, x, cond, uncond, head=None):
+        self.s, self.model, self.head = sampler, model, head
         self.x = x.clone()
         B = x.shape[0]
         self.model_t = torch.zeros((B,), device=x.device, dtype=torch.long)
@@ -224,13 +239,16 @@ class _StepGraph:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture: weight packing, smem attributes, allocator
             for _ in range(2):
-                self.s.p_sample(self.model, self.x, self.model_t, self.t, self.cond, self.uncond, scale, noise=self.noise)
+                _, f = self.s.p_sample(self.model, self.x, self.model_t, self.t, self.cond, self.uncond, scale, noise=self.noise)
+                if self.head is not None:
+                    self.head(f)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out, feats = self.s.p_sample(self.model, self.x, self.model_t, self.t, self.cond, self.uncond, scale,
                                          noise=self.noise)
-        self.graphs[scale] = (g, out, feats)
+            dense = self.head(feats) if self.head is not None else None
+        self.graphs[scale] = (g, out, feats, dense)
 
     def load_cond(self, cond, uncond):
         for k, v in cond.items():
@@ -242,10 +260,12 @@ class _StepGraph:
     def run(self, x, model_t: int, t: int, noise, scale: float):
         if scale not in self.graphs:
             self._capture(scale)
-        g, out, feats = self.graphs[scale]
+        g, out, feats, dense = self.graphs[scale]
         self.x.copy_(x)
         self.model_t.fill_(model_t)
         self.t.fill_(t)
         self.noise.copy_(noise)
         g.replay()
+        if self.head is not None:
+            return out.clone(), feats, dense
         return out.clone(), feats
