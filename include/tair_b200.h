@@ -151,11 +151,11 @@ int tair_blend_tiles(const float* tiles, float* out, int32_t n_tiles, int32_t n_
  * sampling_offsets (M*L*P*2) followed by the raw attention logits (M*L*P) of one query; the kernel applies the
  * softmax over L*P and forms loc = ref + offset/(W,H) (ref_dim 2) or ref_xy + offset/P * ref_wh * 0.5 (ref_dim 4).
  * ref is fp32 [(B,) Lq/q_per_ref, L, ref_dim]; ref_batch_stride (elements) is 0 when shared by all images.
- * value bf16 [B,S,M,D] -> out bf16 [B*Lq, M*D]. */
+ * proj is fp32, or bf16 when proj_bf16 != 0.  value bf16 [B,S,M,D] -> out bf16 [B*Lq, M*D]. */
 int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                    const float* proj, int64_t ldp, const float* ref, int32_t ref_dim, int64_t ref_batch_stride,
-                    int32_t q_per_ref, void* out, int32_t B, int32_t S, int32_t M, int32_t D, int32_t L,
-                    int32_t Lq, int32_t P, void* stream);
+                    const void* proj, int64_t ldp, int32_t proj_bf16, const float* ref, int32_t ref_dim,
+                    int64_t ref_batch_stride, int32_t q_per_ref, void* out, int32_t B, int32_t S, int32_t M,
+                    int32_t D, int32_t L, int32_t Lq, int32_t P, void* stream);
 
 /* Short-sequence multi-head attention (nn.MultiheadAttention core, head_dim 32, L <= 128) on the fused in_proj
  * output qkv [rows, ld] (q | k | v, each H*32 wide); sequence (o, i), o < n_outer, i < n_inner, starts at row
@@ -163,6 +163,15 @@ int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int6
 int tair_mha_small(const void* qkv, int64_t ld, void* out, int64_t ldo, int32_t H, int32_t head_dim, int32_t L,
                    int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride, int64_t tok_stride,
                    float scale, void* stream);
+
+/* Self-attention over many short strided sequences (head slots of 64 columns; narrower heads are zero-padded by the
+ * caller): q/k/v are column offsets into one row-major [rows, ld] bf16 matrix (fused in_proj output); sequence (o, i),
+ * o < n_outer, i < n_inner starts at row o*outer_stride + i*inner_stride, token t at + t*tok_stride.  Output rows
+ * follow the same addressing in o [rows, ldo].  Replaces the nn.MultiheadAttention cores of the TESTR decoder
+ * (deformable_transformer.py:454-466,485-503) without the swapdims copies. */
+int tair_attention_seq_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int32_t H,
+                            int32_t L, int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride,
+                            int64_t tok_stride, float scale, void* stream);
 
 #ifdef __cplusplus
 }

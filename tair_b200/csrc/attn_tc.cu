@@ -35,11 +35,13 @@ constexpr uint32_t AT_SMEM = SM_BAR + 128;
 constexpr uint32_t AT_TMEM_COLS = 256;
 
 struct AttnParams {
-  int B, H, Lq, Lk;
+  int H, Lq, Lk;
+  int n_inner;       // sequences are indexed (outer, inner); plain batched attention has n_inner == 1
   int q_tiles, nblk;
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* o;
   int64_t ldo;
+  int64_t o_outer, o_inner, o_tok;  // output row = outer*o_outer + inner*o_inner + token*o_tok
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -59,7 +61,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
   const int bh = blockIdx.x / p.q_tiles;
-  const int h = bh % p.H, b = bh / p.H;
+  const int h = bh % p.H;
+  const int seq = bh / p.H;
+  const int s_in = seq % p.n_inner, s_out = seq / p.n_inner;
   const int q0 = qt * AT_BM;
 
   if (threadIdx.x == 0) {
@@ -91,13 +95,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
       mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sbase + SM_Q, &tmQ, q_full, h * AT_D, q0, b);
+      tma_load_4d(sbase + SM_Q, &tmQ, q_full, h * AT_D, q0, s_in, s_out);
       for (int j = 0; j < p.nblk; ++j) {
         const int s = j & 1;
         mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
-        tma_load_3d(sbase + SM_K + s * TILE_BYTES, &tmK, kv_full(s), h * AT_D, j * AT_BN, b);
-        tma_load_3d(sbase + SM_V + s * TILE_BYTES, &tmV, kv_full(s), h * AT_D, j * AT_BN, b);
+        tma_load_4d(sbase + SM_K + s * TILE_BYTES, &tmK, kv_full(s), h * AT_D, j * AT_BN, s_in, s_out);
+        tma_load_4d(sbase + SM_V + s * TILE_BYTES, &tmV, kv_full(s), h * AT_D, j * AT_BN, s_in, s_out);
       }
     }
     __syncwarp();
@@ -224,7 +228,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const int q = q0 + r;
     const float inv = 1.f / l_run;
-    __nv_bfloat16* op = p.o + ((int64_t)b * p.Lq + q) * p.ldo + h * AT_D;
+    __nv_bfloat16* op = p.o + ((int64_t)s_out * p.o_outer + (int64_t)s_in * p.o_inner + (int64_t)q * p.o_tok) * p.ldo + h * AT_D;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t ov[32];
@@ -252,11 +256,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int B) {
-  const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)L, (uint64_t)B};
-  const uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
-  const uint32_t box[3] = {AT_D, 128, 1};
-  return make_tmap_bf16(m, base, 3, dims, str, box, nullptr, true);
+// 4-D view (column, token, inner sequence index, outer sequence index) of a row-major [rows, ld] bf16 matrix
+int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int64_t n_inner, int64_t n_outer,
+             int64_t tok_stride, int64_t inner_stride, int64_t outer_stride) {
+  const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)L, (uint64_t)n_inner, (uint64_t)n_outer};
+  // a size-1 dimension never advances; give it any legal (multiple of 16 B, non-zero) stride
+  const uint64_t row = (uint64_t)ld * 2;
+  const uint64_t s1 = (uint64_t)tok_stride * row;
+  const uint64_t s2 = n_inner > 1 ? (uint64_t)inner_stride * row : s1 * (uint64_t)L;
+  const uint64_t s3 = n_outer > 1 ? (uint64_t)outer_stride * row : (s2 > s1 ? s2 : s1) * 2;
+  const uint64_t str[3] = {s1, s2, s3};
+  const uint32_t box[4] = {AT_D, 128, 1, 1};
+  return make_tmap_bf16(m, base, 4, dims, str, box, nullptr, 3);
+}
+
+int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                     int64_t ldo, int H, int Lq, int Lk, int64_t n_outer, int n_inner, int64_t q_outer, int64_t q_inner,
+                     int64_t q_tok, int64_t kv_outer, int64_t kv_inner, int64_t kv_tok, float scale, void* stream) {
+  AttnParams p{};
+  p.H = H; p.Lq = Lq; p.Lk = Lk; p.n_inner = n_inner;
+  p.q_tiles = (Lq + AT_BM - 1) / AT_BM;
+  p.nblk = (Lk + AT_BN - 1) / AT_BN;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  p.o_outer = q_outer; p.o_inner = q_inner; p.o_tok = q_tok;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_map(&tmQ, q, ldq, H * 64, Lq, n_inner, n_outer, q_tok, q_inner, q_outer))) return rc;
+  if ((rc = make_map(&tmK, k, ldk, H * 64, Lk, n_inner, n_outer, kv_tok, kv_inner, kv_outer))) return rc;
+  if ((rc = make_map(&tmV, v, ldv, H * 64, Lk, n_inner, n_outer, kv_tok, kv_inner, kv_outer))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TAIR_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    attr_set = true;
+  }
+  const long grid = (long)n_outer * n_inner * H * p.q_tiles;
+  TAIR_REQUIRE(grid < (1l << 31), "attention: grid too large");
+  attn_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("attn_tc_kernel");
 }
 
 }  // namespace
@@ -276,26 +315,17 @@ extern "C" int tair_attention_bf16(const void* q, int64_t ldq, const void* k, in
                "attention: row stride smaller than H*head_dim");
   for (const void* ptr : {q, k, v, (const void*)o})
     TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention: pointers must be 16-byte aligned");
-  AttnParams p{};
-  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
-  p.q_tiles = (Lq + AT_BM - 1) / AT_BM;
-  p.nblk = (Lk + AT_BN - 1) / AT_BN;
-  p.scale_log2 = scale * 1.4426950408889634f;
-  p.o = reinterpret_cast<__nv_bfloat16*>(o);
-  p.ldo = ldo;
-  CUtensorMap tmQ, tmK, tmV;
-  int rc;
-  if ((rc = make_map(&tmQ, q, ldq, H * 64, Lq, B))) return rc;
-  if ((rc = make_map(&tmK, k, ldk, H * 64, Lk, B))) return rc;
-  if ((rc = make_map(&tmV, v, ldv, H * 64, Lk, B))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAIR_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
-    attr_set = true;
-  }
-  const long grid = (long)B * H * p.q_tiles;
-  TAIR_REQUIRE(grid < (1l << 31), "attention: grid too large");
-  attn_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return check_launch("attn_tc_kernel");
+  return launch_attention(q, ldq, k, ldk, v, ldv, o, ldo, H, Lq, Lk, B, 1, Lq, 0, 1, Lk, 0, 1, scale, stream);
+}
+
+extern "C" int tair_attention_seq_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                                       int32_t H, int32_t L, int64_t n_outer, int32_t n_inner, int64_t outer_stride,
+                                       int64_t inner_stride, int64_t tok_stride, float scale, void* stream) {
+  TAIR_REQUIRE(q && k && v && o, "attention_seq: NULL pointer");
+  TAIR_REQUIRE(H > 0 && L > 0 && n_outer > 0 && n_inner > 0 && tok_stride > 0, "attention_seq: bad shape");
+  TAIR_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ld >= H * 64 && ldo >= H * 64, "attention_seq: bad row strides");
+  for (const void* ptr : {q, k, v, (const void*)o})
+    TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention_seq: pointers must be 16-byte aligned");
+  return launch_attention(q, ld, k, ld, v, ld, o, ldo, H, L, L, n_outer, n_inner, outer_stride, inner_stride,
+                          tok_stride, outer_stride, inner_stride, tok_stride, scale, stream);
 }

@@ -115,7 +115,7 @@ struct MsdaFusedParams {
   const __nv_bfloat16* value;  // [B,S,M,D]
   const int64_t* shapes;
   const int64_t* starts;
-  const float* proj;           // [B*Lq, ldp]: M*L*P*2 offsets then M*L*P logits
+  const void* proj;            // [B*Lq, ldp] fp32 or bf16: M*L*P*2 offsets then M*L*P logits
   int64_t ldp;
   const float* ref;            // [ (B) , Lq/q_per_ref, L, ref_dim ]
   int64_t ref_batch_stride;    // elements; 0 = reference points shared by all images
@@ -128,7 +128,7 @@ struct MsdaFusedParams {
 
 constexpr int MSDA_MAX_LP = 32;
 
-template <int LT, int PT>  // compile-time (levels, points) or 0 for runtime loops
+template <int LT, int PT, typename PJ>  // compile-time (levels, points) or 0 for runtime loops; PJ = proj element type
 __global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p) {
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long item = gtid / p.lanes_per_item;
@@ -140,15 +140,19 @@ __global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p
   const int q = (int)(bq - (long)b * p.Lq);
   const int nL = LT > 0 ? LT : p.L, nP = PT > 0 ? PT : p.P;
   const int LP = nL * nP;
-  const float* row = p.proj + bq * p.ldp;
-  const float* offp = row + (long)m * LP * 2;
-  const float* logit = row + (long)p.M * LP * 2 + (long)m * LP;
+  const PJ* row = reinterpret_cast<const PJ*>(p.proj) + bq * p.ldp;
+  const PJ* offp = row + (long)m * LP * 2;
+  const PJ* logit = row + (long)p.M * LP * 2 + (long)m * LP;
+  auto ldf = [](const PJ* q) -> float {
+    if constexpr (sizeof(PJ) == 4) return __ldg(reinterpret_cast<const float*>(q));
+    else return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(q)));
+  };
   // softmax over the L*P logits of this (query, head)
   float w[LT > 0 ? LT * PT : MSDA_MAX_LP];
   float mx = -3.0e38f;
 #pragma unroll
   for (int i = 0; i < (LT > 0 ? LT * PT : MSDA_MAX_LP); ++i)
-    if (i < LP) { w[i] = __ldg(logit + i); mx = fmaxf(mx, w[i]); }
+    if (i < LP) { w[i] = ldf(logit + i); mx = fmaxf(mx, w[i]); }
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < (LT > 0 ? LT * PT : MSDA_MAX_LP); ++i)
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p
 #pragma unroll
     for (int s = 0; s < (PT > 0 ? PT : 8); ++s) {
       if (s >= nP) break;
-      const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + l * nP + s);
+      const float2 off = make_float2(ldf(offp + 2 * (l * nP + s)), ldf(offp + 2 * (l * nP + s) + 1));
       const float aw = w[l * nP + s] * inv;
       const float h_im = (ry + off.y * sy) * (float)H - 0.5f;
       const float w_im = (rx + off.x * sx) * (float)W - 0.5f;
@@ -238,7 +242,7 @@ extern "C" int tair_msda_forward(const void* value, const int64_t* spatial_shape
 }
 
 extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                               const float* proj, int64_t ldp, const float* ref, int32_t ref_dim,
+                               const void* proj, int64_t ldp, int32_t proj_bf16, const float* ref, int32_t ref_dim,
                                int64_t ref_batch_stride, int32_t q_per_ref, void* out, int32_t B, int32_t S,
                                int32_t M, int32_t D, int32_t L, int32_t Lq, int32_t P, void* stream) {
   TAIR_REQUIRE(value && spatial_shapes && level_start_index && proj && ref && out, "msda_fused: NULL pointer");
@@ -248,7 +252,7 @@ extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes,
   TAIR_REQUIRE(D % 8 == 0 && D <= 256 && (32 % (D / 8)) == 0, "msda_fused: unsupported channels per head %d", D);
   TAIR_REQUIRE(ldp >= (int64_t)M * L * P * 3 && ldp % 2 == 0, "msda_fused: projection row too short");
   TAIR_REQUIRE((reinterpret_cast<uintptr_t>(value) % 16) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 &&
-                   (reinterpret_cast<uintptr_t>(proj) % 8) == 0, "msda_fused: misaligned tensor");
+                   (reinterpret_cast<uintptr_t>(proj) % 4) == 0, "msda_fused: misaligned tensor");
   MsdaFusedParams p{};
   p.value = reinterpret_cast<const __nv_bfloat16*>(value);
   p.shapes = spatial_shapes; p.starts = level_start_index;
@@ -260,8 +264,14 @@ extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes,
   const long threads_total = p.items * p.lanes_per_item;
   const long grid = (threads_total + 255) / 256;
   TAIR_REQUIRE(grid < (1l << 31), "msda_fused: problem too large");
-  if (L == 4 && P == 4) msda_fused_kernel<4, 4><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  else msda_fused_kernel<0, 0><<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (L == 4 && P == 4) {
+    if (proj_bf16) msda_fused_kernel<4, 4, __nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
+    else msda_fused_kernel<4, 4, float><<<(unsigned)grid, 256, 0, st>>>(p);
+  } else {
+    if (proj_bf16) msda_fused_kernel<0, 0, __nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
+    else msda_fused_kernel<0, 0, float><<<(unsigned)grid, 256, 0, st>>>(p);
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("msda_fused_kernel");
 }

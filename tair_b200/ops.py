@@ -374,7 +374,9 @@ def msda_fused(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_in
                q_per_ref: int = 1, ref_shared: bool = False) -> torch.Tensor:
     """value bf16 [B,S,M,D]; proj fp32 [B*Lq, >= M*L*P*3] (raw offsets then raw logits); ref fp32
     [(B,) Lq/q_per_ref, L, 2|4] -> bf16 [B*Lq, M*D]."""
-    _cuda(value, "value", BF16), _cuda(proj, "proj", torch.float32), _cuda(ref, "ref", torch.float32)
+    _cuda(value, "value", BF16), _cuda(proj, "proj"), _cuda(ref, "ref", torch.float32)
+    if proj.dtype not in (torch.float32, BF16):
+        raise TairError("msda_fused: proj must be fp32 or bf16")
     _cuda(spatial_shapes, "spatial_shapes", torch.int64), _cuda(level_start_index, "level_start_index", torch.int64)
     if not (value.is_contiguous() and ref.is_contiguous()):
         raise TairError("msda_fused: value / ref must be contiguous")
@@ -388,7 +390,8 @@ def msda_fused(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_in
     stride = 0 if ref_shared else n_ref * n_levels * ref_dim
     with _timed("msda", 2.0 * out.numel() + 2.0 * value.numel() + 4.0 * p2.shape[0] * M * n_levels * n_points * 3):
         rc = _lib.lib().tair_msda_fused(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                                        p2.data_ptr(), ldp, ref.data_ptr(), ref_dim, stride, q_per_ref, out.data_ptr(),
+                                        p2.data_ptr(), ldp, int(proj.dtype == BF16), ref.data_ptr(), ref_dim, stride,
+                                        q_per_ref, out.data_ptr(),
                                         B, S, M, D, n_levels, Lq, n_points, _stream())
     _lib.check(rc, "tair_msda_fused")
     return out
@@ -404,7 +407,29 @@ def mha_small(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_inner:
     if out is None:
         out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
     o2, ldo = _rows(out, "out")
-    rc = _lib.lib().tair_mha_small(q2.data_ptr(), ld, o2.data_ptr(), ldo, n_heads, hd, L, n_outer, n_inner, outer_stride,
-                                   inner_stride, tok_stride, float(hd ** -0.5), _stream())
+    with _timed("mha_small", 4.0 * n_outer * n_inner * n_heads * L * L * hd):
+        rc = _lib.lib().tair_mha_small(q2.data_ptr(), ld, o2.data_ptr(), ldo, n_heads, hd, L, n_outer, n_inner,
+                                       outer_stride, inner_stride, tok_stride, float(hd ** -0.5), _stream())
     _lib.check(rc, "tair_mha_small")
+    return out
+
+
+def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_inner: int, outer_stride: int,
+                  inner_stride: int, tok_stride: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Self-attention over many short strided sequences on the tcgen05 flash kernel.  qkv bf16 [rows, 3*H*64]
+    (q | k | v, 64-column head slots, narrower heads zero-padded); returns [rows, H*64] in the same row order."""
+    _cuda(qkv, "qkv", BF16)
+    q2, ld = _rows(qkv, "qkv")
+    E = n_heads * 64
+    if q2.shape[1] != 3 * E:
+        raise TairError(f"attention_seq: expected {3 * E} columns, got {q2.shape[1]}")
+    if out is None:
+        out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
+    o2, ldo = _rows(out, "out")
+    base = q2.data_ptr()
+    with _timed("attention_seq", 4.0 * n_outer * n_inner * n_heads * L * L * 64):
+        rc = _lib.lib().tair_attention_seq_bf16(base, base + 2 * E, base + 4 * E, ld, o2.data_ptr(), ldo, n_heads, L,
+                                                n_outer, n_inner, outer_stride, inner_stride, tok_stride, float(scale),
+                                                _stream())
+    _lib.check(rc, "tair_attention_seq_bf16")
     return out

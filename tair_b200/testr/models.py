@@ -76,7 +76,9 @@ class MSDeformAttn(nn.Module):
     def core(self, q2d, pos_rows, rows_per_group, src2d, B, Lq, shapes, starts, ref, ref_shared, q_per_ref):
         """q2d [B*Lq,256] bf16 (WITHOUT pos); pos_rows fp32 [G,384] = Linear_cat(pos) + bias; -> attn output rows."""
         w_bf16, _, _ = self.cat_weight()
-        proj = ops.gemm(q2d, w_bf16, rowgroup=pos_rows, rows_per_group=rows_per_group, out_dtype=F32)
+        # bf16 is ample for the raw offsets (|offset| of a few pixels -> 1e-2 px resolution) and logits; the positional
+        # term is still added in fp32 inside the epilogue before the single rounding
+        proj = ops.gemm(q2d, w_bf16, rowgroup=pos_rows, rows_per_group=rows_per_group)
         value = self.value_proj(src2d)
         S = src2d.shape[0] // B
         return ops.msda_fused(value.view(B, S, self.n_heads, self.d_model // self.n_heads), shapes, starts, proj, ref,
@@ -121,17 +123,39 @@ class MultiheadAttention(nn.Module):
         nn.init.xavier_uniform_(self.in_proj_weight)
 
     def packed(self):
-        """bf16 in_proj weight, fp32 in_proj weight with the V rows zeroed (positional terms reach q,k only), fp32 bias."""
-        st = (self.in_proj_weight.data_ptr(), self.in_proj_weight._version, self.in_proj_bias._version)
+        """Kernel layout with every 32-wide head zero-padded to a 64-column slot (the tcgen05 attention kernel works on
+        64-wide heads; the zero half contributes nothing to Q.K and produces zero output columns):
+        (in_proj bf16 [3*H*64, E], same with the V rows zeroed — positional terms reach q,k only — in bf16 and fp32,
+         padded fp32 bias [3*H*64], out_proj weight bf16 [E, H*64] with zero columns, out_proj bias fp32)."""
+        st = (self.in_proj_weight.data_ptr(), self.in_proj_weight._version, self.in_proj_bias._version,
+              self.out_proj._stamp())
         if getattr(self, "_pk_stamp", None) != st:
             with torch.no_grad():
-                w = self.in_proj_weight.detach().float()
-                wqk = w.clone()
-                wqk[2 * self.embed_dim:] = 0
-                self._pk = (w.to(BF16).contiguous(), wqk.to(BF16).contiguous(), wqk.contiguous(),
-                            self.in_proj_bias.detach().float().contiguous())
+                E, H = self.embed_dim, self.num_heads
+                hd = E // H
+                assert hd <= 64
+                w = self.in_proj_weight.detach().float().view(3, H, hd, E)
+                b = self.in_proj_bias.detach().float().view(3, H, hd)
+                wp = w.new_zeros(3, H, 64, E)
+                wp[:, :, :hd] = w
+                bp = b.new_zeros(3, H, 64)
+                bp[:, :, :hd] = b
+                wqk = wp.clone()
+                wqk[2] = 0
+                wo = self.out_proj.weight.detach().float().view(E, H, hd)
+                wop = wo.new_zeros(E, H, 64)
+                wop[:, :, :hd] = wo
+                self._pk = (wp.reshape(3 * H * 64, E).to(BF16).contiguous(),
+                            wqk.reshape(3 * H * 64, E).to(BF16).contiguous(),
+                            wqk.reshape(3 * H * 64, E).contiguous(), bp.reshape(-1).contiguous(),
+                            wop.reshape(E, H * 64).to(BF16).contiguous(),
+                            self.out_proj.bias.detach().float().contiguous())
             self._pk_stamp = st
         return self._pk
+
+    @property
+    def scale(self) -> float:
+        return (self.embed_dim // self.num_heads) ** -0.5
 
 
 class EncoderLayer(nn.Module):
@@ -181,16 +205,16 @@ class CompositeDecoderLayer(nn.Module):
         (bias included) entering the in_proj / sampling projections; rpg = n_pt (per object) or -n_pt (periodic)."""
         g = lambda name: getattr(self, name + sfx)  # noqa: E731
         intra, inter, cross = g("attn_intra"), g("attn_inter"), g("attn_cross")
-        w_in, _, _, _ = intra.packed()
+        w_in, _, _, _, w_out, b_out = intra.packed()
         qkv = ops.gemm(tgt, w_in, rowgroup=qk_rows, rows_per_group=rpg)
-        a = ops.mha_small(qkv, n_heads=self.n_heads, L=n_pt, n_outer=B * n_obj, n_inner=1, outer_stride=n_pt,
-                          inner_stride=0, tok_stride=1)
-        tgt = g("norm_intra")(intra.out_proj(a, residual=tgt))
-        w_in, _, _, b_in = inter.packed()
+        a = ops.attention_seq(qkv, n_heads=self.n_heads, L=n_pt, n_outer=B * n_obj, n_inner=1, outer_stride=n_pt,
+                              inner_stride=0, tok_stride=1, scale=intra.scale)
+        tgt = g("norm_intra")(ops.gemm(a, w_out, bias=b_out, residual=tgt))
+        w_in, _, _, b_in, w_out, b_out = inter.packed()
         qkv = ops.gemm(tgt, w_in, bias=b_in)
-        a = ops.mha_small(qkv, n_heads=self.n_heads, L=n_obj, n_outer=B, n_inner=n_pt, outer_stride=n_obj * n_pt,
-                          inner_stride=1, tok_stride=n_pt)
-        tgt = g("norm_inter")(inter.out_proj(a, residual=tgt))
+        a = ops.attention_seq(qkv, n_heads=self.n_heads, L=n_obj, n_outer=B, n_inner=n_pt, outer_stride=n_obj * n_pt,
+                              inner_stride=1, tok_stride=n_pt, scale=inter.scale)
+        tgt = g("norm_inter")(ops.gemm(a, w_out, bias=b_out, residual=tgt))
         a = cross.core(tgt, cross_rows, rpg, mem, B, n_obj * n_pt, shapes, starts, boxes_ref, False, n_pt)
         tgt = g("norm_cross")(cross.output_proj(a, residual=tgt))
         return g("norm3")(g("linear2")(g("linear1")(tgt, act=ops.ACT_RELU), residual=tgt))
@@ -330,7 +354,7 @@ class TESTR(nn.Module):
             text_pos = torch.cat((sin_inp.sin(), sin_inp.cos()), dim=-1)[:, :d]                          # [25,256]
             dec_text_rows = []
             for layer in T.decoder.layers:
-                _, _, wqk32, b_in = layer.attn_intra_text.packed()
+                _, _, wqk32, b_in, _, _ = layer.attn_intra_text.packed()
                 _, wc32, bc32 = layer.attn_cross_text.cat_weight()
                 dec_text_rows.append(((text_pos @ wqk32.t() + b_in).contiguous(), (text_pos @ wc32.t() + bc32).contiguous()))
             c = dict(stamp=st, S=S, shapes=shp, starts=starts, enc_ref=enc_ref, props_logit=props_logit,
@@ -377,7 +401,7 @@ class TESTR(nn.Module):
         tgt_text = self.text_embed.weight.to(BF16)[None].expand(B * n_obj, n_ch, d).reshape(-1, d).contiguous()
         boxes_ref = boxes[:, :, None, :].expand(B, n_obj, self.num_feature_levels, 4).contiguous()
         for layer, (txt_qk, txt_cross) in zip(T.decoder.layers, c["dec_text_rows"]):
-            _, wqk_bf16, _, b_in = layer.attn_intra.packed()
+            _, wqk_bf16, _, b_in, _, _ = layer.attn_intra.packed()
             loc_qk = ops.gemm(qpos, wqk_bf16, bias=b_in, out_dtype=F32)                                  # [B*100,768]
             wc_bf16, _, bc = layer.attn_cross.cat_weight()
             loc_cross = ops.gemm(qpos, wc_bf16, bias=bc, out_dtype=F32)                                  # [B*100,384]

@@ -52,6 +52,13 @@ def test_msda_fused_vs_oracle(cuda_lib):
     loc = r[:, :, None, :, None, :2] + off / 4 * r[:, :, None, :, None, 2:] * 0.5
     out = ops.msda_fused(value, shp, start, proj, ref4, B=B, Lq=Lq, n_heads=8, n_levels=4, n_points=4, q_per_ref=25)
     assert rel(out, msda.msda_core(value.float(), shapes, loc, aw).view(B * Lq, 256)) < 1e-2
+    # bf16 projection rows (what the TESTR layers feed it): same math on the bf16-rounded offsets / logits
+    pb = proj.bfloat16()
+    off = pb.float()[:, :256].view(B, Lq, 8, 4, 4, 2)
+    aw = torch.softmax(pb.float()[:, 256:].view(B, Lq, 8, 16), -1).view(B, Lq, 8, 4, 4)
+    loc = r[:, :, None, :, None, :2] + off / 4 * r[:, :, None, :, None, 2:] * 0.5
+    out = ops.msda_fused(value, shp, start, pb, ref4, B=B, Lq=Lq, n_heads=8, n_levels=4, n_points=4, q_per_ref=25)
+    assert rel(out, msda.msda_core(value.float(), shapes, loc, aw).view(B * Lq, 256)) < 1e-2
 
 
 @pytest.mark.parametrize("L,n_outer,n_inner", [(16, 200, 1), (25, 100, 1), (100, 2, 16), (100, 2, 25), (128, 3, 1)])
@@ -76,6 +83,36 @@ def test_mha_small_vs_torch(cuda_lib, L, n_outer, n_inner):
     if n_inner > 1:
         ref = ref.view(n_outer, n_inner, L, E).permute(0, 2, 1, 3)
     assert rel(out, ref.reshape(rows, E)) < 1e-2
+
+
+@pytest.mark.parametrize("L,n_outer,n_inner", [(16, 200, 1), (25, 100, 1), (100, 2, 16), (100, 2, 25)])
+def test_attention_seq_padded_heads_vs_torch(cuda_lib, L, n_outer, n_inner):
+    """tcgen05 attention on strided short sequences with 32-wide heads zero-padded to 64-column slots."""
+    import torch.nn.functional as F
+    from tair_b200 import ops
+    H = 8
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rows = n_outer * L * n_inner
+    real = torch.randn(rows, 3, H, 32, device="cuda", generator=g).bfloat16()
+    qkv = torch.zeros(rows, 3, H, 64, device="cuda", dtype=torch.bfloat16)
+    qkv[..., :32] = real
+    qkv = qkv.view(rows, 3 * H * 64)
+    if n_inner == 1:
+        out = ops.attention_seq(qkv, n_heads=H, L=L, n_outer=n_outer, n_inner=1, outer_stride=L, inner_stride=0,
+                                tok_stride=1, scale=32 ** -0.5)
+        x = real.float().view(n_outer, L, 3, H, 32)
+    else:
+        out = ops.attention_seq(qkv, n_heads=H, L=L, n_outer=n_outer, n_inner=n_inner, outer_stride=L * n_inner,
+                                inner_stride=1, tok_stride=n_inner, scale=32 ** -0.5)
+        x = real.float().view(n_outer, L, n_inner, 3, H, 32).permute(0, 2, 1, 3, 4, 5).reshape(n_outer * n_inner, L, 3, H, 32)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2)          # [seq, L, H, 32]
+    if n_inner > 1:
+        ref = ref.reshape(n_outer, n_inner, L, H, 32).permute(0, 2, 1, 3, 4)
+    ref = ref.reshape(rows, H, 32)
+    got = out.view(rows, H, 64)
+    assert got[..., 32:].abs().max() == 0
+    assert rel(got[..., :32], ref) < 1e-2
 
 
 def test_msdeformattn_module_dropin_signature(detector):

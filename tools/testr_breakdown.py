@@ -1,0 +1,27 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tair_b200 import ops
+from tair_b200.init import nondegenerate_init_
+from tair_b200.testr import TransformerDetector, default_cfg
+dev = torch.device("cuda:0")
+det = TransformerDetector(default_cfg("cuda")).to(dev).eval(); nondegenerate_init_(det, 99)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+g = torch.Generator(device=dev).manual_seed(0)
+feats = [torch.randn(s, device=dev, generator=g).bfloat16() for s in ((B, 16, 16, 1280), (B, 32, 32, 1280), (B, 64, 64, 640), (B, 64, 64, 320))]
+for _ in range(2): det.testr(feats)
+torch.cuda.synchronize()
+t = ops.KernelTimer(); ops.set_timer(t)
+a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+a.record(); det.testr(feats); b.record()
+ops.set_timer(None); torch.cuda.synchronize()
+print("total eager ms", a.elapsed_time(b))
+for k, v in sorted(t.summary().items(), key=lambda kv: -kv[1]["ms"]):
+    print(f"{k:12s} launches={v['launches']:4d} ms={v['ms']:.3f}")
+# per-shape GEMM list
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for (ea, eb, w) in t.records.get("gemm", []):
+    agg[int(w)][0] += 1; agg[int(w)][1] += ea.elapsed_time(eb)
+for w, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
+    print(f"gemm flops={w/1e9:8.2f}G n={n:3d} ms={ms:.3f} -> {w*n/ms/1e9:.0f} TFLOP/s")
