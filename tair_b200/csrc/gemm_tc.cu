@@ -44,7 +44,7 @@ struct GemmParams {
   int conv;        // 0 plain, 1 conv3x3
   int kb_per_tap;  // Cin / 64
   int Ho, Wo, stride;
-  int vec_out, vec_res;
+  int vec_out, vec_res, vec_rg;
   int tma_store;  // bf16 output eligible for the TMA-store epilogue
   int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the whole epilogue body, 4 load B once
   tair_epilogue epi;
@@ -252,11 +252,22 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         tmem_ld_32x32(taddr + c0 + g, r);
         tmem_ld_wait();
         if (n + 32 <= p.N) {
+          if (rg != nullptr && p.vec_rg) {
+            // per-row add rows (positional projections): every lane reads its own row, so use 16-byte loads
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rg + n) + q);
+              r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + t.x);
+              r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + t.y);
+              r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + t.z);
+              r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + t.w);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float a = __uint_as_float(r[j]);
             if (e.bias != nullptr) a += __ldg(e.bias + n + j);
-            if (rg != nullptr) a += __ldg(rg + n + j);
+            if (rg != nullptr && !p.vec_rg) a += __ldg(rg + n + j);
             v[j] = apply_act<ACT>(a);
           }
         } else {
@@ -577,6 +588,7 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   }
   const int esz = e->out_fp32 ? 4 : 2;
   p.vec_out = ((reinterpret_cast<uintptr_t>(e->out) % 16) == 0) && ((e->ldc * esz) % 16 == 0);
+  p.vec_rg = e->rowgroup && ((reinterpret_cast<uintptr_t>(e->rowgroup) % 16) == 0) && (e->ldg % 4 == 0);
   p.vec_res = e->residual && ((reinterpret_cast<uintptr_t>(e->residual) % 16) == 0) &&
               ((e->ldr * 2) % 16 == 0);
   return TAIR_OK;
