@@ -199,7 +199,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC64,
                                                   const CUtensorMap* tmC32, int m0q, int tn, int half, int lane,
-                                                  uint32_t taddr, uint8_t* stg, uint32_t tempty_bar_addr) {
+                                                  uint32_t taddr, uint8_t* stg, uint32_t tempty_bar_addr,
+                                                  bool remote_arrive = false) {
   const tair_epilogue& e = p.epi;
   constexpr bool GEGLU = (ACT == TAIR_ACT_GEGLU);
   constexpr int NT = GEGLU ? BN / 2 : BN;      // output columns produced by this tile
@@ -216,10 +217,14 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   const uint32_t stg_u32 = smem_u32(stg);
   const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
 
+  auto release = [&]() {  // tempty lives in the leader CTA of a pair when remote_arrive is set
+    if (remote_arrive) mbar_arrive_cluster(tempty_bar_addr);
+    else mbar_arrive(tempty_bar_addr);
+  };
   if (half >= NSUB) {  // nothing to drain for this warp (narrow tiles): just release the accumulator
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar_addr);
+    if (lane == 0) release();
     return;
   }
 #pragma unroll 1
@@ -315,7 +320,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     fence_async_smem();            // staging writes -> visible to the TMA (async proxy)
     __syncwarp();
     if (lane == 0) {
-      if (last) mbar_arrive(tempty_bar_addr);
+      if (last) release();
       if (!(p.dbg & 1)) {
         tma_store_2d(ncol == 64 ? tmC64 : tmC32, stg_u32, n_out0 + c0, m0q);
         tma_store_commit();
@@ -499,6 +504,197 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 2-CTA variant: a CTA pair (one cluster, two SMs of a TPC) computes 256 x BN tiles with tcgen05.mma.cta_group::2.
+// CTA r of the pair loads rows [128r, 128r+128) of A and rows [r*BN/2, (r+1)*BN/2) of the weight tile; the leader
+// (rank 0) issues the MMAs for both, each SM accumulating its own 128 rows in its own TMEM.  Per-SM shared-memory
+// operand traffic per K=16 step drops from 4 KB + BN*32 B to 4 KB + BN*16 B for twice the math, which takes the
+// BN=160 convolution tiles off the smem-bandwidth limit (115 -> 82 B/clk).
+template <int BN>
+struct Cfg2 {
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : ((BN >= 160) ? 7 : 8);
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + STG_BYTES;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC64, const __grid_constant__ CUtensorMap tmC32,
+                const GemmParams p) {
+  using C = Cfg2<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // leader only is waited on; one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(empty_bar(s), 1);  // MMA commit is multicast to both CTAs
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * EPI_WARPS);  // leader's copy collects the epilogue warps of both CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(smem_u32(tmem_slot), C::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int tiles_m2 = (p.tiles_m + 1) >> 1;  // 256-row tiles
+  const int num_tiles = tiles_m2 * p.tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tm2 = tile / p.tiles_n, tn = tile - tm2 * p.tiles_n;
+        const int m0 = (tm2 * 2 + (int)rank) * BM, n0 = tn * BN + (int)rank * (BN / 2);
+        int img = 0, ho0 = 0, wo0 = 0;
+        if (p.conv) {
+          const int hw = p.Ho * p.Wo;
+          img = m0 / hw;
+          const int rem = m0 - img * hw;
+          ho0 = rem / p.Wo;
+          wo0 = rem - ho0 * p.Wo;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t full_leader = mapa_shared(full_bar(stage), 0);
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          if (!p.conv) {
+            tma_load_2d_2cta(a_dst, &tmA, full_leader, kb * BK, m0);
+          } else {
+            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tma_load_4d_2cta(a_dst, &tmA, full_leader, cb * BK, wo0 * p.stride + dx - 1, ho0 * p.stride + dy - 1, img);
+          }
+          tma_load_2d_2cta(b_dst, &tmB, full_leader, kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit_2cta(empty_bar(stage), 3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(tfull_bar(acc), 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quad = ew & 3;
+    const int half = ew >> 2;
+    const tair_epilogue& e = p.epi;
+    uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int tm2 = tile / p.tiles_n, tn = tile - tm2 * p.tiles_n;
+      const int m0q = (tm2 * 2 + (int)rank) * BM + quad * 32;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const uint32_t tempty_leader = leader ? tempty_bar(acc) : mapa_shared(tempty_bar(acc), 0);
+      switch (e.act) {
+        case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
+        case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
+        case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
+        case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
+        default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / barriers must stay alive until every remote arrive and TMA signal landed
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch_bn2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
+               const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TAIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Cfg2<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles2 = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  int pairs = num_sms() / 2;
+  if (tiles2 < pairs) pairs = tiles2;
+  gemm_tc2_kernel<BN><<<2 * pairs, GEMM_THREADS, Cfg2<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC64, tmC32, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("gemm_tc2_kernel");
+}
+
 template <int BN>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
               const GemmParams& p, cudaStream_t st) {
@@ -543,12 +739,29 @@ int pick_bn(int M, int N, int num_kb, int act) {
   return best_bn;
 }
 
+// 2-CTA tiles need the TMA-store epilogue and at least one full 256-row tile per SM pair to pay off
+bool use_2cta(const GemmParams& p, int bn) {
+  static int mode = -1;  // TAIR_GEMM_2CTA: 0 never, 1 heuristic (default), 2 always when legal
+  if (mode < 0) {
+    const char* e = getenv("TAIR_GEMM_2CTA");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode == 0 || bn < 128) return false;
+  const bool legal = !p.epi.out_fp32 && p.vec_out && !(p.dbg & 6);
+  if (!legal) return false;
+  if (mode == 2) return true;
+  const long tiles2 = (long)((p.tiles_m + 1) / 2) * ((p.N + bn - 1) / bn);
+  return tiles2 >= num_sms() / 2;
+}
+
 int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn,
              cudaStream_t st) {
   CUtensorMap tmB;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  const bool two = use_2cta(p, bn);
   const uint64_t dimsB[2] = {(uint64_t)p.K, (uint64_t)p.N};
   const uint64_t strB[1] = {(uint64_t)ldw * 2};
-  const uint32_t boxB[2] = {BK, (uint32_t)bn};
+  const uint32_t boxB[2] = {BK, (uint32_t)(two ? bn / 2 : bn)};
   int rc = make_tmap_bf16(&tmB, W, 2, dimsB, strB, boxB, nullptr, true);
   if (rc) return rc;
   p.tiles_m = (p.M + BM - 1) / BM;
@@ -563,6 +776,13 @@ int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, 
     const uint32_t box64[2] = {64, 32}, box32[2] = {32, 32};
     if ((rc = make_tmap_bf16(&tmC64, p.epi.out, 2, dimsC, strC, box64, nullptr, 3))) return rc;
     if ((rc = make_tmap_bf16(&tmC32, p.epi.out, 2, dimsC, strC, box32, nullptr, 2))) return rc;
+  }
+  if (two) {
+    switch (bn) {
+      case 256: return launch_bn2<256>(tmA, tmB, tmC64, tmC32, p, st);
+      case 160: return launch_bn2<160>(tmA, tmB, tmC64, tmC32, p, st);
+      case 128: return launch_bn2<128>(tmA, tmB, tmC64, tmC32, p, st);
+    }
   }
   switch (bn) {
     case 256: return launch_bn<256>(tmA, tmB, tmC64, tmC32, p, st);
