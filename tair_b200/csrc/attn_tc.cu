@@ -109,15 +109,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S: A=Q K-major, B=K K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // O: A=P K-major, B=V MN-major
+      constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
       auto issue_s = [&](int j) {
         const int s = j & 1;
         mbar_wait(kv_full(s), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t qa = sbase + SM_Q, ka = sbase + SM_K + s * TILE_BYTES;
+        const uint32_t q_lo = umma_desc_lo(sbase + SM_Q, 16), k_lo = umma_desc_lo(sbase + SM_K + s * TILE_BYTES, 16);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_ss(tm_S, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024),
-                  idesc_s, k != 0);
+          umma_ss_lohi(tm_S, q_lo + 2 * k, k_lo + 2 * k, desc_hi, idesc_s, k != 0);
         umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
@@ -126,10 +126,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int s = j & 1;
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t va = sbase + SM_V + s * TILE_BYTES;
+        const uint32_t v_lo = umma_desc_lo(sbase + SM_V + s * TILE_BYTES, 16);
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)  // A = P from TMEM: 16 bf16 of K per step = 8 columns
-          umma_ts(tm_O, tm_S + k * 8, umma_desc_sw128(va + k * 2048, 16, 1024), idesc_o, (j | k) != 0);
+        for (int k = 0; k < AT_BN / 16; ++k)  // A = P from TMEM: 16 bf16 of K per step = 8 columns; V advances 16 rows
+          umma_ts_lohi(tm_O, tm_S + k * 8, v_lo + k * (2048 >> 4), desc_hi, idesc_o, (j | k) != 0);
         umma_commit(kv_empty(s));
         if (j + 1 < p.nblk) issue_s(j + 1);   // its commit (s_full) also covers the P V just issued
         else umma_commit(o_done);

@@ -46,7 +46,7 @@ struct GemmParams {
   int Ho, Wo, stride;
   int vec_out, vec_res, vec_rg;
   int tma_store;  // bf16 output eligible for the TMA-store epilogue
-  int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the whole epilogue body, 4 load B once
+  int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the epilogue body, 4 / 8 load B / A only for the first tile
   tair_epilogue epi;
 };
 
@@ -54,7 +54,8 @@ template <int BN>
 struct Cfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : ((BN >= 160) ? 5 : ((BN >= 128) ? 6 : 8));
+  static constexpr int FIT = (int)((232448u - 1280u - STG_BYTES) / STAGE_BYTES);  // 227 KB opt-in limit per CTA
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 };
@@ -380,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles && !(p.dbg & 32); tile += gridDim.x) {
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
         const int m0 = tm * BM, n0 = tn * BN;
         int img = 0, ho0 = 0, wo0 = 0;
@@ -394,10 +395,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const bool skip_b = (p.dbg & 4) && tile != (int)blockIdx.x;
-          mbar_expect_tx(full_bar(stage), skip_b ? A_BYTES : C::STAGE_BYTES);
+          const bool skip_a = (p.dbg & 8) && tile != (int)blockIdx.x;
+          mbar_expect_tx(full_bar(stage), (skip_b ? 0u : C::B_BYTES) + (skip_a ? 0u : A_BYTES));
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
-          if (!p.conv) {
+          if (skip_a) {
+          } else if (!p.conv) {
             tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m0);
           } else {
             const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
@@ -417,6 +420,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, 16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -426,17 +431,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          if (!(p.dbg & 32)) {  // dbg 32 (probe): back-to-back MMA issue without the smem pipeline handshake
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
           }
-          umma_commit(empty_bar(stage));
+          const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+          umma_ss_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != 0);
+#pragma unroll
+          for (int k = 1; k < BK / 16; ++k)  // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
+            umma_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
+          if (!(p.dbg & 32)) umma_commit(empty_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -514,7 +519,8 @@ template <int BN>
 struct Cfg2 {
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 6 : ((BN >= 160) ? 7 : 8);
+  static constexpr int FIT = (int)((232448u - 1280u - STG_BYTES) / STAGE_BYTES);
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + STG_BYTES;
 };
@@ -588,17 +594,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t full_leader = mapa_shared(full_bar(stage), 0);
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+          const bool skip_b = (p.dbg & 4) && tile != pair;
+          const bool skip_a = (p.dbg & 8) && tile != pair;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * ((skip_b ? 0u : C::B_BYTES) + (skip_a ? 0u : A_BYTES)));
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
-          if (!p.conv) {
+          if (skip_a) {
+          } else if (!p.conv) {
             tma_load_2d_2cta(a_dst, &tmA, full_leader, kb * BK, m0);
           } else {
             const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
             const int dy = tap / 3, dx = tap - dy * 3;
             tma_load_4d_2cta(a_dst, &tmA, full_leader, cb * BK, wo0 * p.stride + dx - 1, ho0 * p.stride + dy - 1, img);
           }
-          tma_load_2d_2cta(b_dst, &tmB, full_leader, kb * BK, n0);
+          if (!skip_b) tma_load_2d_2cta(b_dst, &tmB, full_leader, kb * BK, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -610,6 +619,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, 16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -621,14 +632,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+          umma_ss_2cta_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != 0);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
-          }
+          for (int k = 1; k < BK / 16; ++k)
+            umma_ss_2cta_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
           umma_commit_2cta(empty_bar(stage), 3);
           if (++stage == STAGES) {
             stage = 0;
@@ -656,6 +665,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const uint32_t tempty_leader = leader ? tempty_bar(acc) : mapa_shared(tempty_bar(acc), 0);
+      if (p.dbg & 2) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(tempty_leader); else mbar_arrive_cluster(tempty_leader); }
+      } else
       switch (e.act) {
         case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
         case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
@@ -711,11 +725,13 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   return check_launch("gemm_tc_kernel");
 }
 
-// Cycles per K=16 step of one 128xBN tile: the larger of the tensor-pipe floor (128*BN/256) and the shared-memory
-// operand read (A 4 KB + B BN*32 B at ~115 B/clk sustained).
+// Cycles per K=16 MMA of one 128xBN tile, as measured on B200 (tools/mma_rate_probe.py, profiles/round1_summary.md):
+//   * an SS-mode M=128 tcgen05.mma costs ~128 cycles whatever N <= 256 is (the A operand is read from shared memory
+//     at 32 B/clk), so narrow N tiles waste the tensor pipe;
+//   * each SM ingests operands from L2 at ~64 B/clk: (4 KB of A + BN*32 B of B) per K=16 step.
 int tile_cost(int bn) {
-  const int mma = bn / 2, smem = (4096 + bn * 32) / 115;
-  return mma > smem ? mma : smem;
+  const int mma = 128, ingest = 64 + bn / 2;
+  return mma > ingest ? mma : ingest;
 }
 
 // Pick the N tile that minimises  waves x (mainloop cycles + fixed per-tile overhead).
@@ -747,11 +763,12 @@ bool use_2cta(const GemmParams& p, int bn) {
     mode = e ? atoi(e) : 1;
   }
   if (mode == 0 || bn < 128) return false;
-  const bool legal = !p.epi.out_fp32 && p.vec_out && !(p.dbg & 6);
+  const bool legal = !p.epi.out_fp32 && p.vec_out;
   if (!legal) return false;
   if (mode == 2) return true;
+  // pays off only for wide, MMA-bound tiles (halves the B ingest per SM): +10 % on 8192^3, nothing on BN=160 convs
   const long tiles2 = (long)((p.tiles_m + 1) / 2) * ((p.N + bn - 1) / bn);
-  return tiles2 >= num_sms() / 2;
+  return bn == 256 && p.num_kb >= 16 && tiles2 >= 2 * (num_sms() / 2);
 }
 
 int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn,
@@ -789,6 +806,9 @@ int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, 
     case 160: return launch_bn<160>(tmA, tmB, tmC64, tmC32, p, st);
     case 128: return launch_bn<128>(tmA, tmB, tmC64, tmC32, p, st);
     case 64: return launch_bn<64>(tmA, tmB, tmC64, tmC32, p, st);
+    case 96: return launch_bn<96>(tmA, tmB, tmC64, tmC32, p, st);
+    case 192: return launch_bn<192>(tmA, tmB, tmC64, tmC32, p, st);
+    case 224: return launch_bn<224>(tmA, tmB, tmC64, tmC32, p, st);
   }
   set_error("gemm: unsupported BN %d", bn);
   return TAIR_ERR_UNSUPPORTED;
@@ -836,7 +856,8 @@ extern "C" int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   const int n_out = (act == TAIR_ACT_GEGLU) ? N / 2 : N;
   int rc = check_epilogue(epi, p, n_out);
   if (rc) return rc;
-  const int bn = pick_bn(M, N, p.num_kb, act);
+  int bn = pick_bn(M, N, p.num_kb, act);
+  if (const char* f = getenv("TAIR_GEMM_BN")) bn = atoi(f);  // bring-up probe only
   TAIR_REQUIRE(bn != 0, "gemm: GEGLU epilogue needs N %% 128 == 0 (N=%d)", N);
   CUtensorMap tmA;
   const uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M};
