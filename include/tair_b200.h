@@ -173,6 +173,13 @@ int tair_attention_seq_bf16(const void* q, const void* k, const void* v, int64_t
                             int32_t L, int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride,
                             int64_t tok_stride, float scale, void* stream);
 
+/* y[r,:] = softmax(scale * x[r,:]) over bf16 rows (cols % 8 == 0, <= 8192); bf16 [R,C] -> [C,R] batched transpose.
+ * Used by the single-head 512-wide VAE attention (terediff/model/vae.py:253-281), evaluated as GEMM-softmax-GEMM. */
+int tair_softmax_rows_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols, float scale,
+                           void* stream);
+int tair_transpose_bf16(const void* in, int64_t ldi, int64_t in_batch_stride, void* out, int64_t ldo,
+                        int64_t out_batch_stride, int32_t batch, int32_t R, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

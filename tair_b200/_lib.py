@@ -67,6 +67,8 @@ SIGNATURES = {
     "tair_msda_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_mha_small": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i64, _i32, _i64, _i64, _i64, _f32, _vp]),
     "tair_attention_seq_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _i32, _i64, _i64, _i64, _f32, _vp]),
+    "tair_softmax_rows_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp]),
+    "tair_transpose_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

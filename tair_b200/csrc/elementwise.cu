@@ -154,6 +154,74 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
   out[i] = __ldg(in + (((int64_t)b * H + (yo >> 1)) * W + (xo >> 1)) * vc + v);
 }
 
+
+// row softmax of a bf16 matrix: y[r, :] = softmax(scale * x[r, :]); one warp per row, values cached in registers
+// (cols <= 8192).  Used by the single-head, 512-wide VAE attention (terediff/model/vae.py:253-281).
+template <int MAXV>
+__global__ void softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                    int64_t ldy, int rows, int cols, float scale_log2) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = cols >> 3;
+  float v[MAXV][8];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * ldx + vi * 8));
+      const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+      v[k][0] = a.x; v[k][1] = a.y; v[k][2] = b.x; v[k][3] = b.y; v[k][4] = c.x; v[k][5] = c.y; v[k][6] = d.x; v[k][7] = d.y;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[k][i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[k][i] = ex2_approx((v[k][i] - mx) * scale_log2); sum += v[k][i]; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      uint4 q;
+      q.x = pack_bf16(v[k][0] * inv, v[k][1] * inv); q.y = pack_bf16(v[k][2] * inv, v[k][3] * inv);
+      q.z = pack_bf16(v[k][4] * inv, v[k][5] * inv); q.w = pack_bf16(v[k][6] * inv, v[k][7] * inv);
+      *reinterpret_cast<uint4*>(y + (int64_t)row * ldy + vi * 8) = q;
+    }
+  }
+}
+
+// bf16 [R, C] (row stride ldi) -> [C, R] (row stride ldo), batched over blockIdx.z; 32x32 smem tiles
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ldi, int64_t in_batch,
+                                      __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t out_batch, int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  in += (int64_t)blockIdx.z * in_batch;
+  out += (int64_t)blockIdx.z * out_batch;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < R && c < C) ? in[(int64_t)r * ldi + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + tx;
+    if (c < C && r < R) out[(int64_t)c * ldo + r] = tile[tx][k];
+  }
+}
+
 }  // namespace
 }  // namespace tair
 
@@ -243,4 +311,35 @@ extern "C" int tair_upsample2x_nhwc(const void* in, void* out, int32_t B, int32_
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("upsample2x_kernel");
+}
+
+extern "C" int tair_softmax_rows_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t cols,
+                                      float scale, void* stream) {
+  TAIR_REQUIRE(x && y && rows > 0 && cols > 0, "softmax_rows: bad arguments");
+  TAIR_REQUIRE(cols % 8 == 0 && cols <= 8192, "softmax_rows: cols must be a multiple of 8 and <= 8192 (got %d)", cols);
+  TAIR_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cols && ldy >= cols && al16(x) && al16(y),
+               "softmax_rows: misaligned rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const float sl2 = scale * 1.4426950408889634f;
+  const int warps = 4, grid = (rows + warps - 1) / warps;
+  const int nvec = cols / 8;
+  if (nvec <= 32) softmax_rows_kernel<1><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
+  else if (nvec <= 128) softmax_rows_kernel<4><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
+  else if (nvec <= 512) softmax_rows_kernel<16><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
+  else softmax_rows_kernel<32><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int tair_transpose_bf16(const void* in, int64_t ldi, int64_t in_batch_stride, void* out, int64_t ldo,
+                                   int64_t out_batch_stride, int32_t batch, int32_t R, int32_t C, void* stream) {
+  TAIR_REQUIRE(in && out && batch > 0 && R > 0 && C > 0 && ldi >= C && ldo >= R, "transpose: bad arguments");
+  dim3 grid((C + 31) / 32, (R + 31) / 32, batch), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), ldi, in_batch_stride, reinterpret_cast<__nv_bfloat16*>(out), ldo,
+      out_batch_stride, R, C);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("transpose_bf16_kernel");
 }

@@ -165,78 +165,60 @@ __global__ void gn_apply_kernel(const GnParams p) {
   }
 }
 
-// ---- LayerNorm: a warp normalises LN_ROWS consecutive rows; each lane keeps its gamma/beta slice in registers
-// across rows (re-loading them per row made the kernel instruction-bound: 62 % SM busy at 21 % DRAM in ncu),
-// row values stay in registers for the two-pass mean / variance ----
-constexpr int LN_ROWS = 1;  // >1 trades latency hiding for fewer gamma/beta loads: measured slower on B200 (1.9 vs 1.3 ms per step)
-
+// ---- LayerNorm: one warp per row, values kept in registers, two-pass mean / variance.  (Variants that hoist
+// gamma/beta into registers or loop several rows per warp were measured slower on B200: 1.7-1.9 ms vs 1.3 ms per
+// denoising step — fewer resident warps to hide the load latency.) ----
 template <int MAXV>  // max 16-byte vectors per lane
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
-                                                        __nv_bfloat16* __restrict__ y, int64_t ldy,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        int M, int C, float eps) {
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                 int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 int M, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int row0 = warp_global * LN_ROWS;
-  if (row0 >= M) return;
+  if (row >= M) return;
   const int nvec = C >> 3;
-  float gg[MAXV][8], bb[MAXV][8];
+  float v[MAXV][8];
+  float s = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int vi = lane + k * 32;
     if (vi < nvec) {
+      load8(x + (int64_t)row * ldx + vi * 8, v[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[k][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      float o8[8];
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      gg[k][0] = g0.x; gg[k][1] = g0.y; gg[k][2] = g0.z; gg[k][3] = g0.w;
-      gg[k][4] = g1.x; gg[k][5] = g1.y; gg[k][6] = g1.z; gg[k][7] = g1.w;
-      bb[k][0] = b0.x; bb[k][1] = b0.y; bb[k][2] = b0.z; bb[k][3] = b0.w;
-      bb[k][4] = b1.x; bb[k][5] = b1.y; bb[k][6] = b1.z; bb[k][7] = b1.w;
-    }
-  }
-  const float invC = 1.f / (float)C;
-  const int rend = (row0 + LN_ROWS < M) ? row0 + LN_ROWS : M;
-#pragma unroll 2
-  for (int row = row0; row < rend; ++row) {
-    float v[MAXV][8];
-    float s = 0.f;
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + k * 32;
-      if (vi < nvec) {
-        load8(x + (int64_t)row * ldx + vi * 8, v[k]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[k][i];
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * invC;
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + k * 32;
-      if (vi < nvec) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[k][i] -= mean;
-          q = fmaf(v[k][i], v[k][i], q);
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * invC + eps);
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + k * 32;
-      if (vi < nvec) {
-        float o8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o8[i] = fmaf(v[k][i] * rstd, gg[k][i], bb[k][i]);
-        store8(y + (int64_t)row * ldy + vi * 8, o8);
-      }
+      for (int i = 0; i < 8; ++i) o8[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
+      store8(y + (int64_t)row * ldy + vi * 8, o8);
     }
   }
 }
@@ -275,7 +257,8 @@ extern "C" int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, c
   const int threads = p.vec_per_row * rpi;
   // the slab partition depends on the image geometry only (never on the batch size), so a tile's statistics — and
   // with them the whole 50-step trajectory — are bit-identical whatever batch / world size it is processed in
-  int slabs = GN_MAX_SLABS;
+  int slabs = HW / (rpi * 8);  // >= 8 rows per thread
+  if (slabs > GN_MAX_SLABS) slabs = GN_MAX_SLABS;
   const int max_slabs = (HW + rpi - 1) / rpi;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
@@ -303,13 +286,12 @@ extern "C" int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, 
                "layernorm: tensors must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int warps = 8;
-  const int grid = (M + warps * LN_ROWS - 1) / (warps * LN_ROWS);
+  const int grid = (M + warps - 1) / warps;
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const int nvec = C / 8;
   if (nvec <= 32) layernorm_kernel<1><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   else if (nvec <= 64) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
-  else if (nvec <= 96) layernorm_kernel<3><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   else if (nvec <= 160) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

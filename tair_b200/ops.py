@@ -433,3 +433,27 @@ def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_in
                                                 _stream())
     _lib.check(rc, "tair_attention_seq_bf16")
     return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, "x", BF16)
+    x2, ldx = _rows(x, "x")
+    if out is None:
+        out = torch.empty_like(x2)
+    o2, ldy = _rows(out, "out")
+    rc = _lib.lib().tair_softmax_rows_bf16(x2.data_ptr(), ldx, o2.data_ptr(), ldy, x2.shape[0], x2.shape[1], float(scale), _stream())
+    _lib.check(rc, "tair_softmax_rows_bf16")
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """bf16 [batch, R, C] (or [R, C]) contiguous -> [batch, C, R]."""
+    _cuda(x, "x", BF16)
+    if not x.is_contiguous():
+        raise TairError("transpose: x must be contiguous")
+    x3 = x if x.dim() == 3 else x[None]
+    Bn, R, Cc = x3.shape
+    out = torch.empty((Bn, Cc, R), device=x.device, dtype=BF16)
+    rc = _lib.lib().tair_transpose_bf16(x3.data_ptr(), Cc, R * Cc, out.data_ptr(), R, R * Cc, Bn, R, Cc, _stream())
+    _lib.check(rc, "tair_transpose_bf16")
+    return out if x.dim() == 3 else out[0]
