@@ -82,12 +82,14 @@ typedef struct tair_epilogue {
 int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
                    int32_t K, const tair_epilogue* epi, void* stream);
 
-/* 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM:
+/* 3x3 convolution, stride 1 or 2, as an implicit GEMM:
  *   x  [B, H, W, Cin] bf16 channels-last (Cin % 64 == 0)
  *   w  [Cout, 9*Cin]  bf16, K ordered (ky, kx, ci)
+ *   pad = zeros on the top/left (0 or 1); one zero row/column is always available on the bottom/right.
+ *         pad 1 == PyTorch padding=1; pad 0 == F.pad(x,(0,1,0,1)) + padding=0 (VAE downsampler).
  *   out rows are output pixels in (b, ho, wo) order; M = B*Ho*Wo, N = Cout. */
 int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_t H, int32_t W, int32_t Cin,
-                      int32_t Cout, int32_t stride, const tair_epilogue* epi, void* stream);
+                      int32_t Cout, int32_t stride, int32_t pad, const tair_epilogue* epi, void* stream);
 
 /* softmax(Q K^T * scale) V per (batch, head); flash-style, head_dim must be 64.
  *   q [B*Lq, ldq], k/v [B*Lk, ldk/ldv], o [B*Lq, ldo]  bf16; head h occupies columns [64h, 64h+64)

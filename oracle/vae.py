@@ -70,6 +70,33 @@ def vae_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
     return _conv(sd, D + ".conv_out", _swish(_gn(sd, D + ".norm_out", h)))
 
 
+def vae_encode_moments(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.encode up to the posterior parameters — vae.py:573-577, Encoder.forward :399-427,
+    Downsample.forward :50-57 (zero pad right/bottom, stride-2 conv without padding)."""
+    E = "encoder"
+    h = _conv(sd, E + ".conv_in", x)
+    lvl = 0
+    while any(k.startswith(f"{E}.down.{lvl}.") for k in sd):
+        i = 0
+        while (f"{E}.down.{lvl}.block.{i}.norm1.weight") in sd:
+            h = _resblock(sd, f"{E}.down.{lvl}.block.{i}", h)
+            i += 1
+        if (f"{E}.down.{lvl}.downsample.conv.weight") in sd:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"{E}.down.{lvl}.downsample.conv.weight"],
+                         sd[f"{E}.down.{lvl}.downsample.conv.bias"], stride=2)
+        lvl += 1
+    h = _resblock(sd, E + ".mid.block_1", h)
+    h = _attn(sd, E + ".mid.attn_1", h)
+    h = _resblock(sd, E + ".mid.block_2", h)
+    h = _conv(sd, E + ".conv_out", _swish(_gn(sd, E + ".norm_out", h)))
+    return _conv(sd, "quant_conv", h)
+
+
+def image_to_latent(sd: SD, img01: torch.Tensor, scale_factor: float = 0.18215) -> torch.Tensor:
+    """prepare_condition's c_img (cldm.py:143-158): mode of the posterior of (img*2-1), times the latent scale."""
+    return vae_encode_moments(sd, img01 * 2 - 1)[:, :4] * scale_factor
+
+
 def latent_to_image(sd: SD, z: torch.Tensor, scale_factor: float = 0.18215) -> torch.Tensor:
     """ControlLDM.vae_decode + the clamp of val_patches.py:369: clamp((decode(z / s) + 1) / 2, 0, 1)."""
     return ((vae_decode(sd, z / scale_factor) + 1) / 2).clamp(0, 1)

@@ -43,7 +43,7 @@ struct GemmParams {
   int tiles_m, tiles_n, num_kb;
   int conv;        // 0 plain, 1 conv3x3
   int kb_per_tap;  // Cin / 64
-  int Ho, Wo, stride;
+  int Ho, Wo, stride, pad;
   int vec_out, vec_res, vec_rg;
   int tma_store;  // bf16 output eligible for the TMA-store epilogue
   int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the epilogue body, 4 / 8 load B / A only for the first tile
@@ -405,8 +405,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
             const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * BK, wo0 * p.stride + dx - 1,
-                        ho0 * p.stride + dy - 1, img);
+            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * BK, wo0 * p.stride + dx - p.pad,
+                        ho0 * p.stride + dy - p.pad, img);
           }
           if (!skip_b) tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
           if (++stage == STAGES) {
@@ -605,7 +605,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
             const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d_2cta(a_dst, &tmA, full_leader, cb * BK, wo0 * p.stride + dx - 1, ho0 * p.stride + dy - 1, img);
+            tma_load_4d_2cta(a_dst, &tmA, full_leader, cb * BK, wo0 * p.stride + dx - p.pad, ho0 * p.stride + dy - p.pad, img);
           }
           if (!skip_b) tma_load_2d_2cta(b_dst, &tmB, full_leader, kb * BK, n0);
           if (++stage == STAGES) {
@@ -869,7 +869,7 @@ extern "C" int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
 }
 
 extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_t H, int32_t W,
-                                 int32_t Cin, int32_t Cout, int32_t stride, const tair_epilogue* epi,
+                                 int32_t Cin, int32_t Cout, int32_t stride, int32_t pad, const tair_epilogue* epi,
                                  void* stream) {
   TAIR_REQUIRE(x && w, "conv3x3: NULL operand");
   TAIR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: bad shape");
@@ -877,8 +877,10 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   TAIR_REQUIRE(Cin % 64 == 0, "conv3x3: Cin must be a multiple of 64 (got %d)", Cin);
   TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(w) % 16) == 0,
                "conv3x3: operands must be 16-byte aligned");
-  // PyTorch conv arithmetic, k=3, pad=1
-  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  TAIR_REQUIRE(pad == 0 || pad == 1, "conv3x3: pad (top/left) must be 0 or 1 (got %d)", pad);
+  // k=3; `pad` zeros on the top/left, one zero row/column on the bottom/right: pad=1 is PyTorch padding=1, pad=0 is the
+  // asymmetric F.pad(x,(0,1,0,1)) + padding=0 of the VAE downsampler (terediff/model/vae.py:51-55)
+  const int Ho = (H + pad + 1 - 3) / stride + 1, Wo = (W + pad + 1 - 3) / stride + 1;
   // An M tile is 128 consecutive output pixels = bn images x bh rows x bw columns.
   const int bw = Wo < BM ? Wo : BM;
   TAIR_REQUIRE(BM % bw == 0 && Wo % bw == 0, "conv3x3: output width %d does not tile 128", Wo);
@@ -893,7 +895,7 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   p.M = B * Ho * Wo; p.N = Cout; p.K = 9 * Cin;
   p.num_kb = 9 * (Cin / BK);
   p.conv = 1; p.kb_per_tap = Cin / BK;
-  p.Ho = Ho; p.Wo = Wo; p.stride = stride;
+  p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.pad = pad;
   const int act = epi ? epi->act : 0;
   TAIR_REQUIRE(act != TAIR_ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
   int rc = check_epilogue(epi, p, Cout);

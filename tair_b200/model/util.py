@@ -75,9 +75,11 @@ class Conv3x3(nn.Conv2d, _PackMixin):
     UNet / ControlNet (unet.py:491-497, controlnet.py:168-175) therefore run on a 64-channel padded latent.
     """
 
-    def __init__(self, cin, cout, stride=1):
-        super().__init__(cin, cout, 3, stride=stride, padding=1)
+    def __init__(self, cin, cout, stride=1, asymmetric_pad=False):
+        # asymmetric_pad: nn.Conv2d(padding=0) applied after F.pad(x, (0,1,0,1)) — the VAE downsampler (vae.py:40-55)
+        super().__init__(cin, cout, 3, stride=stride, padding=0 if asymmetric_pad else 1)
         self.cin_pad = _round_up(cin, 64)
+        self.pad_lo = 0 if asymmetric_pad else 1
 
     def _pack(self):
         w = self.weight.detach()
@@ -88,7 +90,7 @@ class Conv3x3(nn.Conv2d, _PackMixin):
 
     def forward(self, x: torch.Tensor, *, residual=None, rowgroup=None, rows_per_group=0, out=None, out_dtype=BF16):
         w, b = self.packed()
-        return ops.conv3x3(x, w, stride=self.stride[0], bias=b, residual=residual, rowgroup=rowgroup,
+        return ops.conv3x3(x, w, stride=self.stride[0], pad=self.pad_lo, bias=b, residual=residual, rowgroup=rowgroup,
                            rows_per_group=rows_per_group, out=out, out_dtype=out_dtype)
 
 

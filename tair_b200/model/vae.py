@@ -1,11 +1,12 @@
-"""AutoencoderKL decoder on the sm_100a kernels (SURVEY.md §8f "next", rank 1).
+"""AutoencoderKL (encoder + decoder) on the sm_100a kernels (SURVEY.md §8f "next", rank 1).
 
 Mirrors terediff/model/vae.py — ``ResnetBlock`` (:60-121), ``SDPAttnBlock`` (:232-281), ``Upsample`` (:24-37),
 ``Decoder`` (:429-559), ``AutoencoderKL`` (:562-582) — with the same submodule names, so the reference checkpoint's
 ``decoder.*`` / ``post_quant_conv.*`` keys load unchanged.  The decoder runs once per tile after the 50 denoising steps
 (2.5 TFLOP per tile): GroupNorm(eps 1e-6)+swish -> implicit-GEMM conv3x3 with the residual fused into the epilogue,
 nearest x2 upsampling, and the single-head 512-wide mid attention evaluated as GEMM -> row softmax -> GEMM
-(head_dim 512 does not fit the 64-wide flash kernel).  The encoder half is not built yet: ``encode`` raises.
+(head_dim 512 does not fit the 64-wide flash kernel).  The encoder (``Encoder`` :284-427, ``Downsample`` :40-57 with its
+asymmetric (0,1,0,1) zero padding done by TMA out-of-bounds fill) runs once per tile in ``prepare_condition``.
 """
 from __future__ import annotations
 
@@ -139,10 +140,78 @@ class Decoder(nn.Module):
         return self.conv_out(self.norm_out(h, act=ops.ACT_SILU))
 
 
-class _EncoderPlaceholder(nn.Module):
-    def forward(self, *a, **k):
-        raise NotImplementedError("the VAE encoder is not on the sm_100a kernels yet (SURVEY.md §8f); attach a torch "
-                                  "encoder for prepare_condition")
+class Downsample(nn.Module):
+    """vae.py:40-57: F.pad(x, (0,1,0,1)) then conv3x3 stride 2 padding 0."""
+
+    def __init__(self, in_channels: int, with_conv: bool = True):
+        super().__init__()
+        assert with_conv
+        self.with_conv = with_conv
+        self.conv = Conv3x3(in_channels, in_channels, stride=2, asymmetric_pad=True)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.conv(x)
+
+
+class Encoder(nn.Module):
+    """vae.py:284-427."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, **ignore_kwargs):
+        super().__init__()
+        if len(attn_resolutions):
+            raise NotImplementedError("tair_b200 VAE encoder covers the TeReDiff config (attn_resolutions: [])")
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.conv_in = Conv3x3(in_channels, ch)
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block = nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+            down = nn.Module()
+            down.block = block
+            down.attn = nn.ModuleList()
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = Conv3x3(block_in, 2 * z_channels if double_z else z_channels)
+
+    def forward(self, x_nhwc: torch.Tensor) -> torch.Tensor:
+        h = self.conv_in(x_nhwc)
+        for i_level in range(self.num_resolutions):
+            for blk in self.down[i_level].block:
+                h = blk(h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample(h)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        return self.conv_out(self.norm_out(h, act=ops.ACT_SILU), out_dtype=torch.float32)
+
+
+class DiagonalGaussianDistribution:
+    """terediff/model/distributions.py:24-60 (mode / sample of the latent posterior)."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+    def sample(self) -> torch.Tensor:
+        return self.mean + self.std * torch.randn_like(self.mean)
 
 
 class AutoencoderKL(nn.Module):
@@ -150,8 +219,10 @@ class AutoencoderKL(nn.Module):
 
     def __init__(self, ddconfig: dict, embed_dim: int):
         super().__init__()
-        self.encoder = _EncoderPlaceholder()
+        self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
+        assert ddconfig["double_z"]
+        self.quant_conv = Conv1x1(2 * ddconfig["z_channels"], 2 * embed_dim)
         self.post_quant_conv = Conv1x1(embed_dim, ddconfig["z_channels"])
         self.embed_dim = embed_dim
         self.z_channels = ddconfig["z_channels"]
@@ -170,8 +241,16 @@ class AutoencoderKL(nn.Module):
             self._pq_stamp = st
         return self._pq
 
-    def encode(self, x):
-        return self.encoder(x)
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> DiagonalGaussianDistribution:
+        """(B,3,H,W) fp32 image in [-1,1] -> posterior over the (B,4,H/8,W/8) latent, as AutoencoderKL.encode."""
+        B, _, H, W = x.shape
+        h = self.encoder(ops.nchw_to_nhwc(x.float(), 64))                       # [B,H/8,W/8,8] fp32
+        hh, ww, cz = h.shape[1], h.shape[2], h.shape[3]
+        # quant_conv is an 8 -> 8 channel 1x1 conv on a tiny tensor: fp32 matmul on the moments (torch; 64 FLOP/pixel)
+        wq = self.quant_conv.weight.detach().reshape(self.quant_conv.out_channels, cz).float()
+        m = h.reshape(-1, cz) @ wq.t() + self.quant_conv.bias.detach().float()
+        return DiagonalGaussianDistribution(m.view(B, hh, ww, -1).permute(0, 3, 1, 2).contiguous())
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:

@@ -135,10 +135,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup
     return out
 
 
-def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, bias=None, residual=None, rowgroup=None,
-            rows_per_group=0, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad: int = 1, bias=None, residual=None,
+            rowgroup=None, rows_per_group=0, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
             out_dtype=BF16) -> torch.Tensor:
-    """3x3 / pad 1 convolution on channels-last bf16: x [B,H,W,Cin], w [Cout, 9*Cin] -> [B,Ho,Wo,Cout]."""
+    """3x3 convolution on channels-last bf16: x [B,H,W,Cin], w [Cout, 9*Cin] -> [B,Ho,Wo,Cout].
+    pad=1: PyTorch padding=1; pad=0: zero row/column on the bottom/right only (VAE downsampler)."""
     _cuda(x, "x", BF16), _cuda(w, "w", BF16)
     if x.dim() != 4 or not x.is_contiguous():
         raise TairError("conv3x3: x must be a contiguous [B,H,W,C] tensor")
@@ -146,7 +147,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, bias=None, res
     Cout = w.shape[0]
     if w.dim() != 2 or w.shape[1] != 9 * Cin or not w.is_contiguous():
         raise TairError(f"conv3x3: w must be contiguous [Cout, 9*Cin], got {tuple(w.shape)}")
-    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    Ho, Wo = (H + pad - 2) // stride + 1, (W + pad - 2) // stride + 1
     M = B * Ho * Wo
     if out is None:
         out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=out_dtype)
@@ -154,7 +155,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, bias=None, res
     r2 = residual.view(M, -1) if (residual is not None and residual.dim() == 4) else residual
     e = _make_epilogue(o2, M, Cout, bias, r2, rowgroup, rows_per_group, act)
     with _timed("conv3x3", 2.0 * M * Cout * 9 * Cin):
-        rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, C.byref(e), _stream())
+        rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, pad, C.byref(e), _stream())
     _lib.check(rc, "tair_conv3x3_bf16")
     return out
 

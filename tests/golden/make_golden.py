@@ -140,17 +140,21 @@ def gen_vae():
     dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
               num_res_blocks=2, attn_resolutions=[], dropout=0.0)
     vae = AutoencoderKL(dd, 4).eval()
-    man = {k: v for k, v in Wt.manifest_of(vae).items() if k.startswith(("decoder.", "post_quant_conv."))}
-    sd = Wt.seeded_state_dict(man)
-    vae.load_state_dict(sd, strict=False)
+    full = Wt.manifest_of(vae)
+    man = {k: v for k, v in full.items() if k.startswith(("decoder.", "post_quant_conv."))}
+    sd = Wt.seeded_state_dict(full)
+    vae.load_state_dict(sd)
     z = seeded((1, 4, 16, 16), 51)
+    x = seeded((1, 3, 64, 64), 52).clamp(-1, 1)
     with torch.no_grad():
         img = vae.decode(z)
+        moments = vae.encode(x).parameters
     import json
     mf = json.load(open(os.path.join(HERE, "manifests.json")))
     mf["vae_decoder"] = man
+    mf["vae"] = full
     json.dump(mf, open(os.path.join(HERE, "manifests.json"), "w"))
-    np.savez_compressed(os.path.join(HERE, "vae_decode.npz"), img=img.numpy()[:, :, ::2, ::2])
+    np.savez_compressed(os.path.join(HERE, "vae_decode.npz"), img=img.numpy()[:, :, ::2, ::2], moments=moments.numpy())
     print("vae_decode: img std", img.std().item(), "keys", len(man))
 
 

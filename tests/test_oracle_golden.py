@@ -127,3 +127,8 @@ def test_vae_decoder_matches_reference_fixture(golden, manifests):
     assert np.abs(img.numpy()[:, :, ::2, ::2] - g["img"]).max() < 1e-3 * max(1.0, np.abs(g["img"]).max())
     a = torch.rand(2, 3, 8, 8)
     assert torch.allclose(vae.psnr(a, a), torch.full((2,), 80.0, dtype=torch.float64))
+    full = weights.seeded_state_dict(manifests["vae"])
+    with torch.no_grad():
+        mom = vae.vae_encode_moments(full, weights.seeded_randn((1, 3, 64, 64), 52).clamp(-1, 1))
+    assert mom.shape == (1, 8, 8, 8)
+    assert np.abs(mom.numpy() - g["moments"]).max() < 1e-3 * max(1.0, np.abs(g["moments"]).max())

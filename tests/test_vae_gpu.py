@@ -18,11 +18,10 @@ def rel(a, b):
 def vae(cuda_lib, manifests):
     from oracle import weights
     from tair_b200.model.vae import AutoencoderKL
-    sd = weights.seeded_state_dict(manifests["vae_decoder"])
+    sd = weights.seeded_state_dict(manifests["vae"])
     m = AutoencoderKL(DD, 4)
-    missing, unexpected = m.load_state_dict(sd, strict=False)
-    assert not unexpected and not missing, (missing, unexpected)
-    assert {k: list(v.shape) for k, v in m.state_dict().items()} == manifests["vae_decoder"]
+    m.load_state_dict(sd)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == manifests["vae"]
     return m.cuda().eval(), {k: v.cuda() for k, v in sd.items()}
 
 
@@ -62,7 +61,27 @@ def test_decode_full_tile_psnr(vae):
     assert p > 35.0, p
 
 
-def test_encoder_is_not_silently_emulated(vae):
-    m, _ = vae
-    with pytest.raises(NotImplementedError):
-        m.encode(torch.zeros(1, 3, 64, 64, device="cuda"))
+def test_encode_vs_reference_fixture_and_oracle(vae, golden):
+    """AutoencoderKL.encode(...).mode(): the c_img branch of prepare_condition (cldm.py:143-158)."""
+    from oracle import vae as OV, weights
+    m, sd = vae
+    g = golden("vae_decode.npz")
+    x = weights.seeded_randn((1, 3, 64, 64), 52).clamp(-1, 1).cuda()
+    post = m.encode(x)
+    assert post.parameters.shape == (1, 8, 8, 8) and post.mode().shape == (1, 4, 8, 8)
+    assert rel(post.parameters.cpu(), torch.from_numpy(g["moments"])) < 4e-2
+    xb = weights.seeded_randn((2, 3, 256, 256), 53).clamp(-1, 1).cuda()
+    with torch.no_grad():
+        ref = OV.vae_encode_moments(sd, xb)
+    assert rel(m.encode(xb).parameters, ref) < 4e-2
+
+
+def test_asymmetric_pad_conv(cuda_lib):
+    import torch.nn.functional as F
+    from tair_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(2, 128, 64, 64, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(128, 128, 3, 3, device="cuda", generator=g) / 34).bfloat16()
+    out = ops.conv3x3(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).reshape(128, -1).contiguous(), stride=2, pad=0)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), stride=2).permute(0, 2, 3, 1)
+    assert out.shape == (2, 32, 32, 128) and rel(out, ref) < 1e-2
