@@ -4,8 +4,8 @@
 IRControlNet on (x_noisy || c_img) -> per-block ``control_scales`` -> controlled UNet.  Both networks exchange
 channels-last bf16 tensors directly; only the public inputs/outputs are (B,C,H,W) fp32.
 
-The VAE and the OpenCLIP text encoder are not on the per-step hot path (SURVEY.md §8f "next"); they can be attached
-as ordinary torch modules (``attach_vae`` / ``attach_clip``) so ``prepare_condition`` / ``vae_decode`` keep working.
+The VAE (``tair_b200.model.vae.AutoencoderKL``, once per tile) is built from ``vae_cfg`` on the same kernels; the OpenCLIP
+text encoder (SURVEY.md §8f "next") is attached as an ordinary torch module (``attach_clip``).
 """
 from __future__ import annotations
 
@@ -20,15 +20,25 @@ from .util import BF16
 
 
 class ControlLDM(nn.Module):
-    def __init__(self, unet_cfg: dict, controlnet_cfg: dict, latent_scale_factor: float = 0.18215, vae_cfg=None,
-                 clip_cfg=None):
+    def __init__(self, unet_cfg: dict, vae_cfg: Optional[dict] = None, clip_cfg: Optional[dict] = None,
+                 controlnet_cfg: Optional[dict] = None, latent_scale_factor: float = 0.18215):
+        """Argument order of the reference constructor (cldm.py:22-31).  ``vae_cfg`` builds the AutoencoderKL on our
+        kernels; ``clip_cfg`` is accepted for signature compatibility — the OpenCLIP text encoder is still an attached
+        torch module (``attach_clip``).  ``ControlLDM(unet_cfg, controlnet_cfg)`` is accepted as a shorthand."""
         super().__init__()
+        if controlnet_cfg is None and isinstance(vae_cfg, dict) and "hint_channels" in vae_cfg:
+            vae_cfg, controlnet_cfg = None, vae_cfg
+        if controlnet_cfg is None:
+            raise ValueError("ControlLDM needs a controlnet_cfg")
         self.unet = ControlledUnetModel(**unet_cfg)
+        self.vae: Optional[nn.Module] = None
+        if vae_cfg is not None:
+            from .vae import AutoencoderKL
+            self.vae = AutoencoderKL(**vae_cfg)
+        self.clip: Optional[nn.Module] = None
         self.controlnet = ControlNet(**controlnet_cfg)
         self.scale_factor = latent_scale_factor
         self.control_scales = [1.0] * 13  # cldm.py:30
-        self.vae: Optional[nn.Module] = None
-        self.clip: Optional[nn.Module] = None
         self.return_nhwc_feats = False  # True: hand channels-last bf16 features to the TESTR head (no round trip)
 
     # -- optional non-hot-path submodules ---------------------------------------------------------
