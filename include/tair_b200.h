@@ -93,10 +93,11 @@ int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_t H, int32_
 
 /* softmax(Q K^T * scale) V per (batch, head); flash-style, head_dim must be 64.
  *   q [B*Lq, ldq], k/v [B*Lk, ldk/ldv], o [B*Lq, ldo]  bf16; head h occupies columns [64h, 64h+64)
- *   of each row (so q/k/v may be column slices of one fused projection buffer). */
+ *   of each row (so q/k/v may be column slices of one fused projection buffer).  causal != 0 (Lq == Lk): query i
+ *   sees keys j <= i only (the attn_mask of the OpenCLIP text transformer). */
 int tair_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                         void* o, int64_t ldo, int32_t B, int32_t H, int32_t Lq, int32_t Lk,
-                        int32_t head_dim, float scale, void* stream);
+                        int32_t head_dim, float scale, int32_t causal, void* stream);
 
 /* ---- memory-bound kernels ------------------------------------------------------------------ */
 

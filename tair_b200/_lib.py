@@ -51,7 +51,7 @@ SIGNATURES = {
     "tair_launch_count_reset": (None, []),
     "tair_gemm_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, C.POINTER(Epilogue), _vp]),
     "tair_conv3x3_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(Epilogue), _vp]),
-    "tair_attention_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "tair_attention_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "tair_groupnorm_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "tair_groupnorm_nhwc": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),
     "tair_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _f32, _vp]),

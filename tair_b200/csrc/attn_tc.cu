@@ -37,6 +37,7 @@ constexpr uint32_t AT_TMEM_COLS = 256;
 struct AttnParams {
   int H, Lq, Lk;
   int n_inner;       // sequences are indexed (outer, inner); plain batched attention has n_inner == 1
+  int causal;        // key j attends only to queries i >= j (OpenCLIP text transformer)
   int q_tiles, nblk;
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* o;
@@ -146,7 +147,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int j = 0; j < p.nblk; ++j) {
       mbar_wait(s_full, j & 1);   // S(j) is complete; in-order tensor pipe => P V(j-1) has retired too
       tc_fence_after();
-      const int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
+      int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
+      if (p.causal) {                // ... or lie above the diagonal for this query row
+        const int lim = q0 + r + 1 - j * AT_BN;
+        kvalid = lim < kvalid ? lim : kvalid;
+      }
       const bool full = kvalid >= AT_BN;
       // the whole S row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait, and is
       // used for both the max and the exponentials (the first version re-read TMEM and stalled on 8 waits per block)
@@ -272,8 +277,10 @@ int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int6
 
 int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                      int64_t ldo, int H, int Lq, int Lk, int64_t n_outer, int n_inner, int64_t q_outer, int64_t q_inner,
-                     int64_t q_tok, int64_t kv_outer, int64_t kv_inner, int64_t kv_tok, float scale, void* stream) {
+                     int64_t q_tok, int64_t kv_outer, int64_t kv_inner, int64_t kv_tok, float scale, int causal,
+                     void* stream) {
   AttnParams p{};
+  p.causal = causal;
   p.H = H; p.Lq = Lq; p.Lk = Lk; p.n_inner = n_inner;
   p.q_tiles = (Lq + AT_BM - 1) / AT_BM;
   p.nblk = (Lk + AT_BN - 1) / AT_BN;
@@ -305,7 +312,7 @@ using namespace tair;
 
 extern "C" int tair_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                    int64_t ldv, void* o, int64_t ldo, int32_t B, int32_t H, int32_t Lq,
-                                   int32_t Lk, int32_t head_dim, float scale, void* stream) {
+                                   int32_t Lk, int32_t head_dim, float scale, int32_t causal, void* stream) {
   TAIR_REQUIRE(q && k && v && o, "attention: NULL pointer");
   TAIR_REQUIRE(head_dim == 64, "attention: tensor-core path is built for head_dim 64 (got %d)", head_dim);
   TAIR_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attention: bad shape");
@@ -315,7 +322,8 @@ extern "C" int tair_attention_bf16(const void* q, int64_t ldq, const void* k, in
                "attention: row stride smaller than H*head_dim");
   for (const void* ptr : {q, k, v, (const void*)o})
     TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention: pointers must be 16-byte aligned");
-  return launch_attention(q, ldq, k, ldk, v, ldv, o, ldo, H, Lq, Lk, B, 1, Lq, 0, 1, Lk, 0, 1, scale, stream);
+  TAIR_REQUIRE(!causal || Lq == Lk, "attention: causal masking needs Lq == Lk");
+  return launch_attention(q, ldq, k, ldk, v, ldv, o, ldo, H, Lq, Lk, B, 1, Lq, 0, 1, Lk, 0, 1, scale, causal ? 1 : 0, stream);
 }
 
 extern "C" int tair_attention_seq_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
@@ -327,5 +335,5 @@ extern "C" int tair_attention_seq_bf16(const void* q, const void* k, const void*
   for (const void* ptr : {q, k, v, (const void*)o})
     TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention_seq: pointers must be 16-byte aligned");
   return launch_attention(q, ld, k, ld, v, ld, o, ldo, H, L, L, n_outer, n_inner, outer_stride, inner_stride,
-                          tok_stride, outer_stride, inner_stride, tok_stride, scale, stream);
+                          tok_stride, outer_stride, inner_stride, tok_stride, scale, 0, stream);
 }

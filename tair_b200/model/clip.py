@@ -1,0 +1,126 @@
+"""OpenCLIP text encoder on the sm_100a kernels (SURVEY.md §8f "next", rank 2; re-run every denoising step to turn the
+recognised text into the next step's cross-attention context, spaced_sampler.py:312-317).
+
+Mirrors ``FrozenOpenCLIPEmbedder`` (terediff/model/clip.py:8-61) over the text half of open_clip's ``CLIP``
+(terediff/model/open_clip/model.py, transformer.py:199-254): same parameter names (``model.token_embedding``,
+``model.positional_embedding``, ``model.transformer.resblocks.N.{ln_1,attn,ln_2,mlp.c_fc,mlp.c_proj}``,
+``model.ln_final``, ``model.text_projection``, ``model.logit_scale``).  Per residual block: LayerNorm -> fused in_proj
+GEMM -> causal tcgen05 attention (16 heads x 64) -> out_proj GEMM (+residual) -> LayerNorm -> c_fc GEMM (+GELU) ->
+c_proj GEMM (+residual).  ``layer='penultimate'`` stops one block early, then ``ln_final`` (clip.py:37-55).
+
+The BPE tokenizer needs open_clip's vocabulary file, which is not shipped here: ``attach_tokenizer`` plugs in any
+callable ``List[str] -> LongTensor[B,77]`` (e.g. ``open_clip.tokenize``); ``forward(tokens)`` takes token ids directly.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Callable, List, Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+from .util import BF16, LayerNorm, Linear
+
+
+class _MHA(nn.Module):
+    """nn.MultiheadAttention parameter container (in_proj_weight / in_proj_bias / out_proj)."""
+
+    def __init__(self, d_model: int, n_head: int):
+        super().__init__()
+        self.embed_dim, self.num_heads = d_model, n_head
+        self.in_proj_weight = nn.Parameter(torch.randn(3 * d_model, d_model) * d_model ** -0.5)
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d_model))
+        self.out_proj = Linear(d_model, d_model)
+
+    def packed(self):
+        st = (self.in_proj_weight.data_ptr(), self.in_proj_weight._version, self.in_proj_bias._version)
+        if getattr(self, "_pk_stamp", None) != st:
+            with torch.no_grad():
+                self._pk = (self.in_proj_weight.detach().to(BF16).contiguous(),
+                            self.in_proj_bias.detach().float().contiguous())
+            self._pk_stamp = st
+        return self._pk
+
+
+class ResidualAttentionBlock(nn.Module):
+    """transformer.py:199-254 (no layer scale, self-attention)."""
+
+    def __init__(self, d_model: int, n_head: int, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.ln_1 = LayerNorm(d_model)
+        self.attn = _MHA(d_model, n_head)
+        self.ln_2 = LayerNorm(d_model)
+        width = int(d_model * mlp_ratio)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", Linear(d_model, width)), ("gelu", nn.GELU()),
+                                              ("c_proj", Linear(width, d_model))]))
+
+    def forward(self, x2d: torch.Tensor, B: int, L: int) -> torch.Tensor:
+        E, H = self.attn.embed_dim, self.attn.num_heads
+        w, b = self.attn.packed()
+        qkv = ops.gemm(self.ln_1(x2d), w, bias=b)
+        a = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B=B, H=H, Lq=L, Lk=L, head_dim=E // H, causal=True)
+        x2d = self.attn.out_proj(a, residual=x2d)
+        return self.mlp.c_proj(self.mlp.c_fc(self.ln_2(x2d), act=ops.ACT_GELU), residual=x2d)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, width: int, layers: int, heads: int):
+        super().__init__()
+        self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads) for _ in range(layers)])
+
+
+class _TextModel(nn.Module):
+    def __init__(self, embed_dim: int, text_cfg: dict):
+        super().__init__()
+        width, ctx = text_cfg["width"], text_cfg["context_length"]
+        if width // text_cfg["heads"] != 64:
+            raise NotImplementedError("tair_b200 CLIP text encoder needs 64-wide heads (width 1024, 16 heads)")
+        self.context_length, self.vocab_size = ctx, text_cfg["vocab_size"]
+        self.positional_embedding = nn.Parameter(torch.randn(ctx, width) * 0.01)
+        self.text_projection = nn.Parameter(torch.randn(width, embed_dim) * width ** -0.5)
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)
+        self.transformer = _Transformer(width, text_cfg["layers"], text_cfg["heads"])
+        self.token_embedding = nn.Embedding(text_cfg["vocab_size"], width)
+        self.ln_final = LayerNorm(width)
+
+
+class FrozenOpenCLIPEmbedder(nn.Module):
+    LAYERS = ["last", "penultimate"]
+
+    def __init__(self, embed_dim, vision_cfg=None, text_cfg=None, layer="last"):
+        super().__init__()
+        assert layer in self.LAYERS
+        self.model = _TextModel(embed_dim, dict(text_cfg))
+        self.layer = layer
+        self.layer_idx = 0 if layer == "last" else 1
+        self._tokenizer: Optional[Callable] = None
+
+    def attach_tokenizer(self, fn: Callable[[List[str]], torch.Tensor]) -> None:
+        self._tokenizer = fn
+
+    @torch.no_grad()
+    def forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        return self.encode_with_transformer(tokens)
+
+    @torch.no_grad()
+    def encode_with_transformer(self, text: torch.Tensor) -> torch.Tensor:
+        """tokens (B,77) int64 -> (B,77,width) fp32 — clip.py:37-45."""
+        m = self.model
+        B, L = text.shape
+        x = (m.token_embedding(text) + m.positional_embedding).to(BF16).reshape(B * L, -1).contiguous()
+        blocks = m.transformer.resblocks
+        for i, blk in enumerate(blocks):
+            if i == len(blocks) - self.layer_idx:
+                break
+            x = blk(x, B, L)
+        return m.ln_final(x).float().view(B, L, -1)
+
+    def encode(self, text: List[str]) -> torch.Tensor:
+        if self._tokenizer is None:
+            raise RuntimeError("FrozenOpenCLIPEmbedder.encode needs a BPE tokenizer: call attach_tokenizer(fn) with a "
+                               "List[str] -> LongTensor[B,77] callable (e.g. open_clip.tokenize)")
+        if isinstance(text, str):
+            text = [text]
+        tokens = self._tokenizer(text).to(next(self.model.parameters()).device)
+        return self(tokens)

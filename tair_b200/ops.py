@@ -169,7 +169,8 @@ def reset_launch_count() -> None:
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, H: int, Lq: int, Lk: int,
-              head_dim: int = 64, scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              head_dim: int = 64, scale: Optional[float] = None, causal: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T * scale) v per (batch, head).
 
     q [B*Lq, >=H*D], k/v [B*Lk, >=H*D] are 2-D bf16 views with unit inner stride (column slices of a fused
@@ -189,7 +190,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, H: i
         scale = head_dim ** -0.5
     with _timed("attention", 4.0 * B * H * Lq * Lk * head_dim):
         rc = _lib.lib().tair_attention_bf16(q2.data_ptr(), ldq, k2.data_ptr(), ldk, v2.data_ptr(), ldv, o2.data_ptr(),
-                                            ldo, B, H, Lq, Lk, head_dim, float(scale), _stream())
+                                            ldo, B, H, Lq, Lk, head_dim, float(scale), int(causal), _stream())
     _lib.check(rc, "tair_attention_bf16")
     return out
 

@@ -158,9 +158,27 @@ def gen_vae():
     print("vae_decode: img std", img.std().item(), "keys", len(man))
 
 
+def gen_clip():
+    H.install()
+    from terediff.model.clip import FrozenOpenCLIPEmbedder
+    m = FrozenOpenCLIPEmbedder(1024, dict(image_size=224, layers=32, width=1280, head_width=80, patch_size=14),
+                               dict(context_length=77, vocab_size=49408, width=1024, heads=16, layers=24),
+                               layer="penultimate").eval()
+    man = Wt.manifest_of(m)
+    m.load_state_dict(Wt.seeded_state_dict(man), strict=False)
+    tokens = torch.randint(0, 49408, (2, 77), generator=torch.Generator().manual_seed(71))
+    with torch.no_grad():
+        z = m(tokens)
+    mf = json.load(open(os.path.join(HERE, "manifests.json")))
+    mf["clip_text"] = man
+    json.dump(mf, open(os.path.join(HERE, "manifests.json"), "w"))
+    np.savez_compressed(os.path.join(HERE, "clip_text.npz"), tokens=tokens.numpy(), z=z.numpy()[:, ::4, ::2])
+    print("clip_text: z std", z.std().item(), "keys", len(man))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["manifest", "unet", "sched", "msda", "merge", "testr"]
     torch.manual_seed(0)
     for w in what:
         {"manifest": gen_manifest, "unet": gen_unet, "sched": gen_sched, "msda": gen_msda, "merge": gen_merge,
-         "testr": gen_testr, "vae": gen_vae}[w]()
+         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip}[w]()

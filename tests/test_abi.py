@@ -49,7 +49,7 @@ def test_argument_validation_without_gpu(lib):
     # NULL operands are rejected before anything touches the device
     rc = lib.tair_gemm_bf16(None, 8, None, 8, 1, 1, 8, None, None)
     assert rc == -1 and b"NULL" in lib.tair_last_error()
-    rc = lib.tair_attention_bf16(1, 64, 1, 64, 1, 64, 1, 64, 1, 1, 1, 1, 32, 1.0, None)
+    rc = lib.tair_attention_bf16(1, 64, 1, 64, 1, 64, 1, 64, 1, 1, 1, 1, 32, 1.0, 0, None)
     assert rc == -1 and b"head_dim" in lib.tair_last_error()
 
 

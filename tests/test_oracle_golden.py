@@ -132,3 +132,13 @@ def test_vae_decoder_matches_reference_fixture(golden, manifests):
         mom = vae.vae_encode_moments(full, weights.seeded_randn((1, 3, 64, 64), 52).clamp(-1, 1))
     assert mom.shape == (1, 8, 8, 8)
     assert np.abs(mom.numpy() - g["moments"]).max() < 1e-3 * max(1.0, np.abs(g["moments"]).max())
+
+
+def test_clip_text_encoder_matches_reference_fixture(golden, manifests):
+    from oracle import clip as OC
+    g = golden("clip_text.npz")
+    sd = weights.seeded_state_dict(manifests["clip_text"])
+    with torch.no_grad():
+        z = OC.encode_tokens(sd, torch.from_numpy(g["tokens"]))
+    assert z.shape == (2, 77, 1024)
+    assert np.abs(z.numpy()[:, ::4, ::2] - g["z"]).max() < 2e-3
