@@ -4,8 +4,8 @@
 IRControlNet on (x_noisy || c_img) -> per-block ``control_scales`` -> controlled UNet.  Both networks exchange
 channels-last bf16 tensors directly; only the public inputs/outputs are (B,C,H,W) fp32.
 
-The VAE (``tair_b200.model.vae.AutoencoderKL``, once per tile) is built from ``vae_cfg`` on the same kernels; the OpenCLIP
-text encoder (SURVEY.md §8f "next") is attached as an ordinary torch module (``attach_clip``).
+The VAE (``tair_b200.model.vae.AutoencoderKL``, once per tile) and the OpenCLIP text encoder
+(``tair_b200.model.clip.FrozenOpenCLIPEmbedder``, once per step) are built from ``vae_cfg`` / ``clip_cfg`` on the same kernels.
 """
 from __future__ import annotations
 
@@ -23,8 +23,8 @@ class ControlLDM(nn.Module):
     def __init__(self, unet_cfg: dict, vae_cfg: Optional[dict] = None, clip_cfg: Optional[dict] = None,
                  controlnet_cfg: Optional[dict] = None, latent_scale_factor: float = 0.18215):
         """Argument order of the reference constructor (cldm.py:22-31).  ``vae_cfg`` builds the AutoencoderKL on our
-        kernels; ``clip_cfg`` is accepted for signature compatibility — the OpenCLIP text encoder is still an attached
-        torch module (``attach_clip``).  ``ControlLDM(unet_cfg, controlnet_cfg)`` is accepted as a shorthand."""
+        kernels and ``clip_cfg`` the OpenCLIP text encoder (``tair_b200.model.clip.FrozenOpenCLIPEmbedder``); either may be
+        None and attached later.  ``ControlLDM(unet_cfg, controlnet_cfg)`` is accepted as a shorthand."""
         super().__init__()
         if controlnet_cfg is None and isinstance(vae_cfg, dict) and "hint_channels" in vae_cfg:
             vae_cfg, controlnet_cfg = None, vae_cfg
@@ -36,6 +36,9 @@ class ControlLDM(nn.Module):
             from .vae import AutoencoderKL
             self.vae = AutoencoderKL(**vae_cfg)
         self.clip: Optional[nn.Module] = None
+        if clip_cfg is not None:
+            from .clip import FrozenOpenCLIPEmbedder
+            self.clip = FrozenOpenCLIPEmbedder(**clip_cfg)
         self.controlnet = ControlNet(**controlnet_cfg)
         self.scale_factor = latent_scale_factor
         self.control_scales = [1.0] * 13  # cldm.py:30

@@ -95,9 +95,16 @@ class FrozenOpenCLIPEmbedder(nn.Module):
         self.layer = layer
         self.layer_idx = 0 if layer == "last" else 1
         self._tokenizer: Optional[Callable] = None
+        self._cache: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self.cache_size = 1024
 
     def attach_tokenizer(self, fn: Callable[[List[str]], torch.Tensor]) -> None:
         self._tokenizer = fn
+        self._cache.clear()
+
+    def clear_cache(self) -> None:
+        """Drop memoised prompt embeddings (call after loading new weights)."""
+        self._cache.clear()
 
     @torch.no_grad()
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:
@@ -117,10 +124,27 @@ class FrozenOpenCLIPEmbedder(nn.Module):
         return m.ln_final(x).float().view(B, L, -1)
 
     def encode(self, text: List[str]) -> torch.Tensor:
+        """clip.py:56-61, batched: the sampler re-encodes one prompt per tile per step and most of them repeat from
+        step to step, so embeddings are memoised by prompt string and only the distinct new strings are run (as one
+        batch) through the transformer."""
         if self._tokenizer is None:
-            raise RuntimeError("FrozenOpenCLIPEmbedder.encode needs a BPE tokenizer: call attach_tokenizer(fn) with a "
-                               "List[str] -> LongTensor[B,77] callable (e.g. open_clip.tokenize)")
+            import os
+            if os.environ.get("TAIR_BPE_VOCAB"):
+                from ..tokenizer import BPETokenizer
+                self._tokenizer = BPETokenizer()
+            else:
+                raise RuntimeError("FrozenOpenCLIPEmbedder.encode needs a BPE tokenizer: set TAIR_BPE_VOCAB to the CLIP "
+                                   "merge table or call attach_tokenizer(fn) with a List[str] -> LongTensor[B,77] callable")
         if isinstance(text, str):
             text = [text]
-        tokens = self._tokenizer(text).to(next(self.model.parameters()).device)
-        return self(tokens)
+        new = [t for t in dict.fromkeys(text) if t not in self._cache]
+        if new:
+            z = self(self._tokenizer(new).to(self.model.positional_embedding.device))
+            for t, row in zip(new, z):
+                self._cache[t] = row
+        out = torch.stack([self._cache[t] for t in text])
+        for t in text:
+            self._cache.move_to_end(t)
+        while len(self._cache) > max(self.cache_size, len(text)):
+            self._cache.popitem(last=False)
+        return out

@@ -176,9 +176,28 @@ def gen_clip():
     print("clip_text: z std", z.std().item(), "keys", len(man))
 
 
+TOKENIZER_CASES = ["", "A realistic scene where the texts \"HELLO\", \"world\" appear clearly on signs.",
+                   "it's  a  test &amp;amp; more!!!  123 4.5", "na\u00efve caf\u00e9 \u2014 \u65e5\u672c\u8a9e", "x" * 400,
+                   "<start_of_text> hi <end_of_text>", "don't we'll I'm they've you'd HE'S", "  \t\n  ",
+                   "exit, 24, OPEN, coffee, P, no-parking"]
+
+
+def gen_tok():
+    H.install()
+    import random
+    import string
+    from terediff.model.open_clip import tokenizer as RT
+    rnd = random.Random(0)
+    cases = TOKENIZER_CASES + ["".join(rnd.choice(string.printable) for _ in range(rnd.randint(0, 120))) for _ in range(40)]
+    ids = RT.tokenize(cases)
+    json.dump({"texts": cases, "ids": [[int(v) for v in row] for row in ids]},
+              open(os.path.join(HERE, "tokenizer_cases.json"), "w"))
+    print("tokenizer_cases:", len(cases))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["manifest", "unet", "sched", "msda", "merge", "testr"]
     torch.manual_seed(0)
     for w in what:
         {"manifest": gen_manifest, "unet": gen_unet, "sched": gen_sched, "msda": gen_msda, "merge": gen_merge,
-         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip}[w]()
+         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip, "tok": gen_tok}[w]()

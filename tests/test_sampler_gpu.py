@@ -164,3 +164,53 @@ def test_val_sample_with_text_spotting_feedback(setup, manifests):
         assert all(isinstance(s, str) and len(s) <= 25 for s in r["pred_texts"])
         assert all(p.shape == (16, 2) and p.dtype == np.int32 for p in r["pred_polys"])
     assert cond["c_txt"].shape == (B, 77, 1024) and not torch.equal(cond["c_txt"], first_ctx)
+
+
+def test_val_sample_with_kernel_clip_encoder(setup, manifests):
+    """Same loop with the real text encoder on the kernels (tair_b200.model.clip) in place of the stand-in: the prompt of
+    every tile is tokenised (hash tokenizer here — the CLIP merge table is not shipped), run through the 23 causal
+    blocks, memoised by prompt string, and conditions the next step."""
+    from types import SimpleNamespace
+    from oracle import clip as OC, weights
+    from tair_b200 import ops
+    from tair_b200.model.clip import FrozenOpenCLIPEmbedder
+    from tair_b200.testr import TransformerDetector, default_cfg
+    m, _, _, sampler, sched = setup
+    det = TransformerDetector(default_cfg("cuda"))
+    det.load_state_dict(weights.seeded_state_dict(manifests["testr"]))
+    det = det.cuda().eval()
+    csd = weights.seeded_state_dict(manifests["clip_text"])
+    clip = FrozenOpenCLIPEmbedder(1024, None, dict(context_length=77, vocab_size=49408, width=1024, heads=16, layers=24),
+                                  layer="penultimate")
+    clip.load_state_dict(csd)
+    clip = clip.cuda().eval()
+
+    def hash_tokenizer(texts):
+        out = torch.zeros((len(texts), 77), dtype=torch.long)
+        for i, s in enumerate(texts):
+            ids = [49406] + [zlib.crc32(w.encode()) % 49000 for w in s.split()][:75] + [49407]
+            out[i, :len(ids)] = torch.tensor(ids)
+        return out
+    clip.attach_tokenizer(hash_tokenizer)
+    old = m.clip
+    m.attach_clip(clip)
+    try:
+        B = 2
+        x_T, c_img, _ = inputs(B, seed=22)
+        cond = dict(c_txt=clip.encode([""] * B), c_img=c_img)
+        assert torch.equal(cond["c_txt"][0], cond["c_txt"][1])
+        cfg = SimpleNamespace(exp_args=SimpleNamespace(mode="VAL", prompt_style="CAPTION"))
+        x, res = sampler.val_sample(m, "cuda", 3, (B, 4, 64, 64), cond, None, 1.0, x_T=x_T, progress=False, cfg=cfg,
+                                    pure_cldm=m, ts_model=det, use_cuda_graph=True)
+        assert torch.isfinite(x).all() and len(res) == 3
+        prompts = res[-1]["batch_prompts"]
+        with torch.no_grad():
+            ref = OC.encode_tokens({k: v.cuda() for k, v in csd.items()}, hash_tokenizer(prompts).cuda())
+        err = ((cond["c_txt"] - ref).abs().max() / ref.abs().max()).item()
+        assert err < 4e-2, err
+        # memoised: encoding prompts that were already seen launches no kernel
+        ops.reset_launch_count()
+        again = clip.encode(prompts)
+        assert ops.launch_count() == 0 and torch.equal(again, cond["c_txt"])
+    finally:
+        m.attach_clip(old)
