@@ -90,53 +90,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tm_S = tmem;
   const uint32_t tm_O = tmem + 128;
 
+  // Warps 0 and 1 run warp-uniform loops and ONE elected lane issues the TMA / tcgen05 instructions, so that ptxas keeps
+  // their operands in uniform registers (a `lane == 0` branch turns each issue into a vote/elect/R2UR loop).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
       mbar_expect_tx(q_full, TILE_BYTES);
       tma_load_4d(sbase + SM_Q, &tmQ, q_full, h * AT_D, q0, s_in, s_out);
-      for (int j = 0; j < p.nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < p.nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
         tma_load_4d(sbase + SM_K + s * TILE_BYTES, &tmK, kv_full(s), h * AT_D, j * AT_BN, s_in, s_out);
         tma_load_4d(sbase + SM_V + s * TILE_BYTES, &tmV, kv_full(s), h * AT_D, j * AT_BN, s_in, s_out);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S: A=Q K-major, B=K K-major
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // O: A=P K-major, B=V MN-major
-      constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(kv_full(s), (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_lo = umma_desc_lo(sbase + SM_Q, 16), k_lo = umma_desc_lo(sbase + SM_K + s * TILE_BYTES, 16);
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S: A=Q K-major, B=K K-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // O: A=P K-major, B=V MN-major
+    constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
+    auto issue_s = [&](int j) {
+      const int s = j & 1;
+      mbar_wait(kv_full(s), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t q_lo = umma_desc_lo(sbase + SM_Q, 16), k_lo = umma_desc_lo(sbase + SM_K + s * TILE_BYTES, 16);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
           umma_ss_lohi(tm_S, q_lo + 2 * k, k_lo + 2 * k, desc_hi, idesc_s, k != 0);
         umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < p.nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t v_lo = umma_desc_lo(sbase + SM_V + s * TILE_BYTES, 16);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < p.nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint32_t v_lo = umma_desc_lo(sbase + SM_V + s * TILE_BYTES, 16);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)  // A = P from TMEM: 16 bf16 of K per step = 8 columns; V advances 16 rows
           umma_ts_lohi(tm_O, tm_S + k * 8, v_lo + k * (2048 >> 4), desc_hi, idesc_o, (j | k) != 0);
         umma_commit(kv_empty(s));
-        if (j + 1 < p.nblk) issue_s(j + 1);   // its commit (s_full) also covers the P V just issued
-        else umma_commit(o_done);
+      }
+      __syncwarp();
+      if (j + 1 < p.nblk) issue_s(j + 1);   // its commit (s_full) also covers the P V just issued
+      else {
+        if (elect_one()) umma_commit(o_done);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;       // query row inside the tile

@@ -232,7 +232,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   for (int s = half; s < NSUB; s += 2) {
     const int c0 = s * 64;
     const int ncol = (NT - c0) < 64 ? (NT - c0) : 64;  // 64, or 32 for the tail of BN = 160
-    if (lane == 0) tma_store_wait_read<0>();           // previous store of this warp has left the staging buffer
+    if (elect_one()) tma_store_wait_read<0>();         // previous store of this warp has left the staging buffer
     __syncwarp();
 #pragma unroll 1
     for (int g = 0; g < ncol; g += 32) {
@@ -320,7 +320,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     if (last) tc_fence_before();   // all TMEM reads of this tile by this warp are done
     fence_async_smem();            // staging writes -> visible to the TMA (async proxy)
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {  // same elected lane every time: bulk-group commit / wait are per-thread state
       if (last) release();
       if (!(p.dbg & 1)) {
         tma_store_2d(ncol == 64 ? tmC64 : tmC32, stg_u32, n_out0 + c0, m0q);
@@ -376,83 +376,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp runs the loop and ONE elected lane issues: with warp-uniform control flow ptxas keeps the TMA /
+    // UMMA operands in uniform registers; a `lane == 0` branch instead makes every UTMALDG / UTCHMMA a
+    // vote-elect-R2UR "waterfall" loop (measured: 93-118 cycles per MMA issue vs 41-60, tools/probes/mma_shape_probe.cu)
+    if (elect_one()) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles && !(p.dbg & 32); tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-        const int m0 = tm * BM, n0 = tn * BN;
-        int img = 0, ho0 = 0, wo0 = 0;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles && !(p.dbg & 32); tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m0 = tm * BM, n0 = tn * BN;
+      int img = 0, ho0 = 0, wo0 = 0;
+      if (p.conv) {
+        const int hw = p.Ho * p.Wo;
+        img = m0 / hw;
+        const int rem = m0 - img * hw;
+        ho0 = rem / p.Wo;
+        wo0 = rem - ho0 * p.Wo;
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const bool skip_b = (p.dbg & 4) && tile != (int)blockIdx.x;
+        const bool skip_a = (p.dbg & 8) && tile != (int)blockIdx.x;
+        const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + A_BYTES;
+        int c0 = kb * BK, c1 = m0, c2 = 0, c3 = 0;
         if (p.conv) {
-          const int hw = p.Ho * p.Wo;
-          img = m0 / hw;
-          const int rem = m0 - img * hw;
-          ho0 = rem / p.Wo;
-          wo0 = rem - ho0 * p.Wo;
+          const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          c0 = cb * BK;
+          c1 = wo0 * p.stride + dx - p.pad;
+          c2 = ho0 * p.stride + dy - p.pad;
+          c3 = img;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const bool skip_b = (p.dbg & 4) && tile != (int)blockIdx.x;
-          const bool skip_a = (p.dbg & 8) && tile != (int)blockIdx.x;
+        if (elect_one()) {
           mbar_expect_tx(full_bar(stage), (skip_b ? 0u : C::B_BYTES) + (skip_a ? 0u : A_BYTES));
-          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + A_BYTES;
           if (skip_a) {
           } else if (!p.conv) {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(a_dst, &tmA, full_bar(stage), c0, c1);
           } else {
-            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * BK, wo0 * p.stride + dx - p.pad,
-                        ho0 * p.stride + dy - p.pad, img);
+            tma_load_4d(a_dst, &tmA, full_bar(stage), c0, c1, c2, c3);
           }
           if (!skip_b) tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-      constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
-      const uint32_t a_lo0 = umma_desc_lo(smem_base, 16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (!(p.dbg & 32)) {  // dbg 32 (probe): back-to-back MMA issue without the smem pipeline handshake
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-          }
-          const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
-          const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
+    const uint32_t a_lo0 = umma_desc_lo(smem_base, 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        if (!(p.dbg & 32)) {  // dbg 32 (probe): back-to-back MMA issue without the smem pipeline handshake
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+        }
+        const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+        if (elect_one()) {
           umma_ss_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != 0);
 #pragma unroll
           for (int k = 1; k < BK / 16; ++k)  // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
             umma_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
           if (!(p.dbg & 32)) umma_commit(empty_bar(stage));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(tfull_bar(acc));
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int quad = ew & 3;   // TMEM lane quadrant (== warp % 4, the only lanes this warp may read)
@@ -497,7 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) tma_store_wait_all<0>();  // bulk stores must have completed before the CTA releases its smem
+    if (elect_one()) tma_store_wait_all<0>();  // bulk stores must have completed before the CTA releases its smem
     __syncwarp();
   }
 
@@ -575,49 +587,58 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_tiles = tiles_m2 * p.tiles_n;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int tm2 = tile / p.tiles_n, tn = tile - tm2 * p.tiles_n;
-        const int m0 = (tm2 * 2 + (int)rank) * BM, n0 = tn * BN + (int)rank * (BN / 2);
-        int img = 0, ho0 = 0, wo0 = 0;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int tm2 = tile / p.tiles_n, tn = tile - tm2 * p.tiles_n;
+      const int m0 = (tm2 * 2 + (int)rank) * BM, n0 = tn * BN + (int)rank * (BN / 2);
+      int img = 0, ho0 = 0, wo0 = 0;
+      if (p.conv) {
+        const int hw = p.Ho * p.Wo;
+        img = m0 / hw;
+        const int rem = m0 - img * hw;
+        ho0 = rem / p.Wo;
+        wo0 = rem - ho0 * p.Wo;
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t full_leader = mapa_shared(full_bar(stage), 0);
+        const bool skip_b = (p.dbg & 4) && tile != pair;
+        const bool skip_a = (p.dbg & 8) && tile != pair;
+        const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + A_BYTES;
+        int c0 = kb * BK, c1 = m0, c2 = 0, c3 = 0;
         if (p.conv) {
-          const int hw = p.Ho * p.Wo;
-          img = m0 / hw;
-          const int rem = m0 - img * hw;
-          ho0 = rem / p.Wo;
-          wo0 = rem - ho0 * p.Wo;
+          const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          c0 = cb * BK;
+          c1 = wo0 * p.stride + dx - p.pad;
+          c2 = ho0 * p.stride + dy - p.pad;
+          c3 = img;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t full_leader = mapa_shared(full_bar(stage), 0);
-          const bool skip_b = (p.dbg & 4) && tile != pair;
-          const bool skip_a = (p.dbg & 8) && tile != pair;
+        if (elect_one()) {
           if (leader) mbar_expect_tx(full_bar(stage), 2 * ((skip_b ? 0u : C::B_BYTES) + (skip_a ? 0u : A_BYTES)));
-          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + A_BYTES;
           if (skip_a) {
           } else if (!p.conv) {
-            tma_load_2d_2cta(a_dst, &tmA, full_leader, kb * BK, m0);
+            tma_load_2d_2cta(a_dst, &tmA, full_leader, c0, c1);
           } else {
-            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d_2cta(a_dst, &tmA, full_leader, cb * BK, wo0 * p.stride + dx - p.pad, ho0 * p.stride + dy - p.pad, img);
+            tma_load_4d_2cta(a_dst, &tmA, full_leader, c0, c1, c2, c3);
           }
           if (!skip_b) tma_load_2d_2cta(b_dst, &tmB, full_leader, kb * BK, n0);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
       constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
       const uint32_t a_lo0 = umma_desc_lo(smem_base, 16);
@@ -634,22 +655,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
           const uint32_t b_lo = a_lo + (A_BYTES >> 4);
-          umma_ss_2cta_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != 0);
+          if (elect_one()) {
+            umma_ss_2cta_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != 0);
 #pragma unroll
-          for (int k = 1; k < BK / 16; ++k)
-            umma_ss_2cta_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
-          umma_commit_2cta(empty_bar(stage), 3);
+            for (int k = 1; k < BK / 16; ++k)
+              umma_ss_2cta_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
+            umma_commit_2cta(empty_bar(stage), 3);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2cta(tfull_bar(acc), 3);
+        if (elect_one()) umma_commit_2cta(tfull_bar(acc), 3);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int quad = ew & 3;
@@ -680,7 +704,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
   }
 
