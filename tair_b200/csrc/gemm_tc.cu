@@ -20,6 +20,10 @@
 #include <cstdlib>
 
 #include "../../include/tair_b200.h"
+#include <cstring>
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace tair {
@@ -749,12 +753,12 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   return check_launch("gemm_tc_kernel");
 }
 
-// Cycles per K=16 MMA of one 128xBN tile, as measured on B200 (tools/mma_rate_probe.py, profiles/round1_summary.md):
-//   * an SS-mode M=128 tcgen05.mma costs ~128 cycles whatever N <= 256 is (the A operand is read from shared memory
-//     at 32 B/clk), so narrow N tiles waste the tensor pipe;
-//   * each SM ingests operands from L2 at ~64 B/clk: (4 KB of A + BN*32 B of B) per K=16 step.
+// Fallback tile choice (used while a stream is being captured, or when autotuning is off / not applicable).
+// Per K=16 step a 128xBN tile costs max(MMA pipe, operand ingest): the tensor pipe needs ~N/2 + 43 cycles for an SS-mode
+// MMA (tools/probes/mma_shape_probe.cu) and each SM ingests TMA operand rows (128 B each) at ~64 B/clk:
+// (4 KB of A + BN*32 B of B) per step.
 int tile_cost(int bn) {
-  const int mma = 128, ingest = 64 + bn / 2;
+  const int mma = bn / 2 + 43, ingest = 64 + bn / 2;
   return mma > ingest ? mma : ingest;
 }
 
@@ -779,27 +783,28 @@ int pick_bn(int M, int N, int num_kb, int act) {
   return best_bn;
 }
 
-// 2-CTA tiles need the TMA-store epilogue and at least one full 256-row tile per SM pair to pay off
+// 2-CTA tiles need the TMA-store epilogue
+bool legal_2cta(const GemmParams& p, int bn) {
+  return (bn == 256 || bn == 160 || bn == 128) && !p.epi.out_fp32 && p.vec_out;
+}
+
+// heuristic: pays off only for wide, MMA-bound tiles with at least one full 256-row tile per SM pair
 bool use_2cta(const GemmParams& p, int bn) {
   static int mode = -1;  // TAIR_GEMM_2CTA: 0 never, 1 heuristic (default), 2 always when legal
   if (mode < 0) {
     const char* e = getenv("TAIR_GEMM_2CTA");
     mode = e ? atoi(e) : 1;
   }
-  if (mode == 0 || bn < 128) return false;
-  const bool legal = !p.epi.out_fp32 && p.vec_out;
-  if (!legal) return false;
+  if (mode == 0 || !legal_2cta(p, bn)) return false;
   if (mode == 2) return true;
-  // pays off only for wide, MMA-bound tiles (halves the B ingest per SM): +10 % on 8192^3, nothing on BN=160 convs
   const long tiles2 = (long)((p.tiles_m + 1) / 2) * ((p.N + bn - 1) / bn);
   return bn == 256 && p.num_kb >= 16 && tiles2 >= 2 * (num_sms() / 2);
 }
 
-int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn,
+int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn, bool two,
              cudaStream_t st) {
   CUtensorMap tmB;
   p.tiles_m = (p.M + BM - 1) / BM;
-  const bool two = use_2cta(p, bn);
   const uint64_t dimsB[2] = {(uint64_t)p.K, (uint64_t)p.N};
   const uint64_t strB[1] = {(uint64_t)ldw * 2};
   const uint32_t boxB[2] = {BK, (uint32_t)(two ? bn / 2 : bn)};
@@ -858,6 +863,107 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   return TAIR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tile autotuner.  Which (BN, 1-CTA / 2-CTA pair) is fastest depends on wave quantisation, on the K depth and on how
+// many SMs share the L2 -> SM operand path; no closed-form rule got within 25 % on every shape of the UNet
+// (tools/bn_sweep.py), so the first call for a problem shape times every legal candidate on the caller's stream
+// (1 warm-up + 5 timed launches each) and caches the winner per device.  All candidates compute bit-identical
+// results (same K order per output element), so tuning never changes the numbers.  Tuning is skipped — and the
+// closed-form pick used, uncached — while the stream is being captured, when the output aliases an input, or when
+// TAIR_AUTOTUNE=0.  It synchronises the stream once per new shape.
+struct TuneKey {
+  int dev, conv, M, N, K, Wo, stride, act, flags;
+  bool operator<(const TuneKey& o) const {
+    return std::memcmp(this, &o, sizeof(TuneKey)) < 0;
+  }
+};
+struct TuneChoice { int bn; bool two; };
+
+std::mutex g_tune_mu;
+std::map<TuneKey, TuneChoice> g_tuned;
+
+bool autotune_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TAIR_AUTOTUNE");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on == 1;
+}
+
+bool overlaps(const void* a, size_t na, const void* b, size_t nb) {
+  const uintptr_t x = reinterpret_cast<uintptr_t>(a), y = reinterpret_cast<uintptr_t>(b);
+  return a && b && x < y + nb && y < x + na;
+}
+
+// Decide the tile for this problem and launch it.  `in_bytes` is the extent of the A operand (aliasing check).
+int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const void* W, int64_t ldw, GemmParams& p,
+                   int act, cudaStream_t st) {
+  p.tiles_m = (p.M + BM - 1) / BM;
+  if (const char* f = getenv("TAIR_GEMM_BN")) {  // bring-up probe only
+    const int bn = atoi(f);
+    return dispatch(tmA, W, ldw, p, bn, use_2cta(p, bn), st);
+  }
+  const int heur = pick_bn(p.M, p.N, p.num_kb, act);
+  TAIR_REQUIRE(heur != 0, "gemm: GEGLU epilogue needs N %% 128 == 0 (N=%d)", p.N);
+  const size_t esz = p.epi.out_fp32 ? 4 : 2;
+  const int n_out = act == TAIR_ACT_GEGLU ? p.N / 2 : p.N;
+  const size_t out_bytes = ((size_t)(p.M - 1) * p.epi.ldc + n_out) * esz;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool tunable = autotune_enabled() && act != TAIR_ACT_GEGLU && p.dbg == 0 &&
+                       cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone &&
+                       !overlaps(p.epi.out, out_bytes, A, in_bytes) &&
+                       !overlaps(p.epi.out, out_bytes, p.epi.residual, p.epi.residual ? ((size_t)(p.M - 1) * p.epi.ldr + n_out) * 2 : 0);
+  TuneKey key;
+  std::memset(&key, 0, sizeof(key));
+  cudaGetDevice(&key.dev);
+  key.conv = p.conv; key.M = p.M; key.N = p.N; key.K = p.K; key.Wo = p.Wo; key.stride = p.stride; key.act = act;
+  key.flags = (p.epi.out_fp32 ? 1 : 0) | (p.vec_out ? 2 : 0) | (p.epi.residual ? 4 : 0) | (p.epi.rowgroup ? 8 : 0);
+  {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    auto it = g_tuned.find(key);
+    if (it != g_tuned.end()) return dispatch(tmA, W, ldw, p, it->second.bn, it->second.two, st);
+  }
+  if (!tunable) return dispatch(tmA, W, ldw, p, heur, use_2cta(p, heur), st);
+
+  const int cands[7] = {256, 224, 192, 160, 128, 96, 64};
+  cudaEvent_t e0, e1;
+  TAIR_CUDA(cudaEventCreate(&e0));
+  TAIR_CUDA(cudaEventCreate(&e1));
+  const int64_t launches_before = g_launch_count.load();
+  TuneChoice best{heur, use_2cta(p, heur)};
+  float best_ms = -1.f;
+  int rc = TAIR_OK;
+  for (int i = 0; i < 7 && rc == TAIR_OK; ++i) {
+    for (int two = 0; two < 2 && rc == TAIR_OK; ++two) {
+      const int bn = cands[i];
+      if (two && !legal_2cta(p, bn)) continue;
+      if ((long)p.tiles_m * ((p.N + bn - 1) / bn) > 8L * num_sms() && bn < 128) continue;  // hopeless: skip
+      if ((rc = dispatch(tmA, W, ldw, p, bn, two != 0, st))) break;  // warm-up (also sets the smem attribute)
+      cudaEventRecord(e0, st);
+      for (int r = 0; r < 5 && rc == TAIR_OK; ++r) rc = dispatch(tmA, W, ldw, p, bn, two != 0, st);
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { rc = check_launch("gemm autotune"); if (rc == TAIR_OK) rc = TAIR_ERR_CUDA; break; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (best_ms < 0.f || ms < best_ms) { best_ms = ms; best = TuneChoice{bn, two != 0}; }
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  g_launch_count.store(launches_before);  // tuning launches are not part of the caller's work
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    g_tuned[key] = best;
+  }
+  if (getenv("TAIR_AUTOTUNE_VERBOSE"))
+    fprintf(stderr, "[tair autotune] %s M=%d N=%d K=%d act=%d -> BN=%d%s (%.1f us; closed-form pick BN=%d)\n",
+            p.conv ? "conv" : "gemm", p.M, p.N, p.K, act, best.bn, best.two ? " 2-CTA" : "", best_ms / 5 * 1e3, heur);
+  return dispatch(tmA, W, ldw, p, best.bn, best.two, st);
+}
+
 }  // namespace
 }  // namespace tair
 
@@ -880,16 +986,13 @@ extern "C" int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   const int n_out = (act == TAIR_ACT_GEGLU) ? N / 2 : N;
   int rc = check_epilogue(epi, p, n_out);
   if (rc) return rc;
-  int bn = pick_bn(M, N, p.num_kb, act);
-  if (const char* f = getenv("TAIR_GEMM_BN")) bn = atoi(f);  // bring-up probe only
-  TAIR_REQUIRE(bn != 0, "gemm: GEGLU epilogue needs N %% 128 == 0 (N=%d)", N);
   CUtensorMap tmA;
   const uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M};
   const uint64_t strA[1] = {(uint64_t)lda * 2};
   const uint32_t boxA[2] = {BK, BM};
   rc = make_tmap_bf16(&tmA, A, 2, dimsA, strA, boxA, nullptr, true);
   if (rc) return rc;
-  return dispatch(tmA, W, ldw, p, bn, static_cast<cudaStream_t>(stream));
+  return tuned_dispatch(tmA, A, ((size_t)(M - 1) * lda + K) * 2, W, ldw, p, act, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_t H, int32_t W,
@@ -924,8 +1027,6 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   TAIR_REQUIRE(act != TAIR_ACT_GEGLU, "conv3x3: GEGLU epilogue not supported");
   int rc = check_epilogue(epi, p, Cout);
   if (rc) return rc;
-  const int bn = pick_bn(p.M, p.N, p.num_kb, act);
-
   CUtensorMap tmA;
   const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strA[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
@@ -933,5 +1034,5 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   rc = make_tmap_bf16(&tmA, x, 4, dimsA, strA, boxA, es, true);
   if (rc) return rc;
-  return dispatch(tmA, w, (int64_t)9 * Cin, p, bn, static_cast<cudaStream_t>(stream));
+  return tuned_dispatch(tmA, x, (size_t)B * H * W * Cin * 2, w, (int64_t)9 * Cin, p, act, static_cast<cudaStream_t>(stream));
 }

@@ -48,8 +48,14 @@ class ControlLDM(nn.Module):
     def attach_vae(self, vae: nn.Module) -> None:
         self.vae = vae
 
-    def attach_clip(self, clip: nn.Module) -> None:
-        self.clip = clip
+    def attach_clip(self, clip) -> None:
+        """Plug in a text encoder: a module (registered as a child) or any object with ``encode(list[str])``."""
+        self._modules.pop("clip", None)
+        self.__dict__.pop("clip", None)
+        if isinstance(clip, nn.Module) or clip is None:
+            self.clip = clip
+        else:
+            object.__setattr__(self, "clip", clip)
 
     @torch.no_grad()
     def vae_decode(self, z: torch.Tensor) -> torch.Tensor:

@@ -23,6 +23,7 @@ class KernelTimer:
 
     def __init__(self):
         self.records = {}   # family -> list of (start_event, end_event, work)
+        self.shapes = {}    # family -> list of shape tags, parallel to records
 
     def summary(self):
         torch.cuda.synchronize()
@@ -30,6 +31,18 @@ class KernelTimer:
         for fam, recs in self.records.items():
             ms = sum(a.elapsed_time(b) for a, b, _ in recs)
             out[fam] = dict(launches=len(recs), ms=ms, work=sum(w for _, _, w in recs))
+        return out
+
+    def by_shape(self):
+        """(family, shape tag) -> launches / ms / work, for tools/shape_breakdown.py."""
+        torch.cuda.synchronize()
+        out = {}
+        for fam, recs in self.records.items():
+            for (a, b, w), tag in zip(recs, self.shapes[fam]):
+                d = out.setdefault((fam, tag), dict(launches=0, ms=0.0, work=0.0))
+                d["launches"] += 1
+                d["ms"] += a.elapsed_time(b)
+                d["work"] += w
         return out
 
 
@@ -42,10 +55,10 @@ def set_timer(t: Optional[KernelTimer]) -> None:
 
 
 class _timed:
-    __slots__ = ("fam", "work", "a")
+    __slots__ = ("fam", "work", "a", "tag")
 
-    def __init__(self, fam: str, work: float):
-        self.fam, self.work = fam, work
+    def __init__(self, fam: str, work: float, tag=None):
+        self.fam, self.work, self.tag = fam, work, tag
 
     def __enter__(self):
         if _timer is not None:
@@ -57,6 +70,7 @@ class _timed:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
             _timer.records.setdefault(self.fam, []).append((self.a, b, self.work))
+            _timer.shapes.setdefault(self.fam, []).append(self.tag)
         return False
 
 
@@ -129,7 +143,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
     e = _make_epilogue(out, M, n_out, bias, residual, rowgroup, rows_per_group, act)
-    with _timed("gemm", 2.0 * M * N * K):
+    with _timed("gemm", 2.0 * M * N * K, (M, N, K, act)):
         rc = _lib.lib().tair_gemm_bf16(a2.data_ptr(), lda, w2.data_ptr(), ldw, M, N, K, C.byref(e), _stream())
     _lib.check(rc, "tair_gemm_bf16")
     return out
@@ -154,7 +168,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad: int = 1, 
     o2 = out.view(M, -1) if out.dim() == 4 else out
     r2 = residual.view(M, -1) if (residual is not None and residual.dim() == 4) else residual
     e = _make_epilogue(o2, M, Cout, bias, r2, rowgroup, rows_per_group, act)
-    with _timed("conv3x3", 2.0 * M * Cout * 9 * Cin):
+    with _timed("conv3x3", 2.0 * M * Cout * 9 * Cin, (B, H, W, Cin, Cout, stride)):
         rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, pad, C.byref(e), _stream())
     _lib.check(rc, "tair_conv3x3_bf16")
     return out
@@ -188,7 +202,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, H: i
     o2, ldo = _rows(out, "out")
     if scale is None:
         scale = head_dim ** -0.5
-    with _timed("attention", 4.0 * B * H * Lq * Lk * head_dim):
+    with _timed("attention", 4.0 * B * H * Lq * Lk * head_dim, (B, H, Lq, Lk)):
         rc = _lib.lib().tair_attention_bf16(q2.data_ptr(), ldq, k2.data_ptr(), ldk, v2.data_ptr(), ldv, o2.data_ptr(),
                                             ldo, B, H, Lq, Lk, head_dim, float(scale), int(causal), _stream())
     _lib.check(rc, "tair_attention_bf16")
@@ -222,7 +236,7 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, group
     if out is None:
         out = torch.empty_like(x)
     ws = _gn_workspace(x.device, B, groups)
-    with _timed("groupnorm", 6.0 * x.numel()):  # bytes: two reads + one write of a bf16 tensor
+    with _timed("groupnorm", 6.0 * x.numel(), tuple(x.shape)):  # bytes: two reads + one write of a bf16 tensor
         rc = _lib.lib().tair_groupnorm_nhwc(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, HW, C,
                                             groups, float(eps), act, ws.data_ptr(), _stream())
     _lib.check(rc, "tair_groupnorm_nhwc")
@@ -236,7 +250,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     if out is None:
         out = torch.empty((x2.shape[0], x2.shape[1]), device=x.device, dtype=BF16)
     o2, ldy = _rows(out, "out")
-    with _timed("layernorm", 4.0 * x2.numel()):  # bytes: one read + one write
+    with _timed("layernorm", 4.0 * x2.numel(), tuple(x2.shape)):  # bytes: one read + one write
         rc = _lib.lib().tair_layernorm(x2.data_ptr(), ldx, o2.data_ptr(), ldy, gamma.data_ptr(), beta.data_ptr(),
                                        x2.shape[0], x2.shape[1], float(eps), _stream())
     _lib.check(rc, "tair_layernorm")
