@@ -262,6 +262,9 @@ def main():
     mt = torch.full((BATCH,), 500, device=dev, dtype=torch.long)
     tt = torch.full((BATCH,), 25, device=dev, dtype=torch.long)
     cond = dict(c_txt=c_txt, c_img=c_img)
+    # one stream for this measurement: with the ControlNet on its own stream two kernels can share the GPU and the
+    # per-launch event times would no longer be per-kernel times
+    overlap, model.overlap_controlnet = model.overlap_controlnet, False
     for _ in range(2):
         sampler.p_sample(model, x_T, mt, tt, cond, None, 1.0)
     torch.cuda.synchronize()
@@ -269,6 +272,7 @@ def main():
     ops.set_timer(timer)
     sampler.p_sample(model, x_T, mt, tt, cond, None, 1.0)
     ops.set_timer(None)
+    model.overlap_controlnet = overlap
     fam = timer.summary()
     launches_per_step = ops.launch_count()
     pk = peaks()
@@ -277,7 +281,10 @@ def main():
     n_conv = conv["launches"]
     roofline = {"kernel": "gemm_tc_kernel<BN> (implicit-GEMM 3x3 conv, tcgen05/TMA)", "bound": "tensor",
                 "achieved": conv_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                "frac": conv_tflops / pk["tc_sustained"], "traffic": None,
+                "frac": conv_tflops / pk["tc_sustained"],
+                # ncu dram__bytes_read+write of ONE launch of the most frequent conv (B=16, 64x64, 320->320;
+                # profiles/round1_summary.md): 45.7 MB against 42+42 MB algorithmic in+out — the output stays in L2
+                "traffic": 45.7e6, "traffic_unit": "B per launch (64x64 320->320 conv, ncu --set full)",
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_denoise_step": n_conv, "avg_launch_ms": conv["ms"] / n_conv,
                 "flop_per_launch_avg": conv["work"] / n_conv}

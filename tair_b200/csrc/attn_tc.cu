@@ -3,19 +3,24 @@
 // Replaces F.scaled_dot_product_attention at terediff/model/attention.py:206
 // (SDPCrossAttention.forward :189-216): softmax(Q K^T * scale) V per (batch, head).
 //
-// One CTA = one (batch, head, 128-query tile); two CTAs are co-resident per SM so that one
-// CTA's softmax (CUDA cores / MUFU) overlaps the other's tensor-core work.
-//   warp 0       TMA producer: Q once, then K/V blocks of 128 keys into a 2-stage ring
+// One CTA = one (batch, head, 128-query tile); two CTAs are co-resident per SM.
+//   warp 0       TMA producer: Q once, then K blocks (128 keys) into a 3-stage ring and V blocks into a 2-stage ring
 //   warp 1       TMEM owner + MMA issuer: S = Q K^T (SS, M128 N128 K64) and O += P V (TS: P read from TMEM)
-//   warps 2..5   softmax: one thread per query row; S read with tcgen05.ld; P = exp2(S*c - m) written back as
-//                packed bf16 with tcgen05.st over the S columns it has already consumed
+//   warps 2..5   softmax: one thread per query row; S read with tcgen05.ld; P = exp2(S*c - m) written as packed bf16
+//                with tcgen05.st into its own TMEM columns
+// Software pipeline: as soon as the softmax threads hold S(j) in registers (`s_free`) the MMA warp issues
+// S(j+1) = Q K(j+1)^T, which therefore runs UNDER the exponentials of block j; P(j) V follows when P(j) is written.
+// The softmax warps then go from block to block without waiting for the tensor pipe (the earlier layout aliased P
+// over S, which serialised softmax(j) -> P V(j) -> S(j+1) and left the MUFU pipe 40 % idle, profiles/round1_summary.md).
 // O accumulates in TMEM across key blocks; the running maximum is updated lazily (only when a block's maximum
 // exceeds it by more than 2^8, so exp2 arguments stay <= 8), in which case the softmax threads rescale O in TMEM.
-// TMEM (256 columns): S fp32 [0,128) aliased by P bf16x2 [0,64) | O fp32 [128,192).
+// TMEM (256 columns): S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256).
 #include <atomic>
 #include <math_constants.h>
 
 #include "../../include/tair_b200.h"
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tair {
@@ -28,10 +33,11 @@ constexpr int AT_D = 64;     // head dim
 constexpr int AT_THREADS = 192;
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;  // 16 KB: one 128-row x 64-col bf16 tile
 constexpr uint32_t SM_Q = 0;
-constexpr uint32_t SM_K = SM_Q + TILE_BYTES;          // 2 stages
-constexpr uint32_t SM_V = SM_K + 2 * TILE_BYTES;      // 2 stages
-constexpr uint32_t SM_BAR = SM_V + 2 * TILE_BYTES;
-constexpr uint32_t AT_SMEM = SM_BAR + 128;
+constexpr int K_STAGES = 3, V_STAGES = 2;
+constexpr uint32_t SM_K = SM_Q + TILE_BYTES;
+constexpr uint32_t SM_V = SM_K + K_STAGES * TILE_BYTES;
+constexpr uint32_t SM_BAR = SM_V + V_STAGES * TILE_BYTES;
+constexpr uint32_t AT_SMEM = SM_BAR + 144;
 constexpr uint32_t AT_TMEM_COLS = 256;
 
 struct AttnParams {
@@ -52,12 +58,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar = sbase + SM_BAR;
   const uint32_t q_full = bar + 0;
-  const uint32_t s_full = bar + 8;
-  const uint32_t p_full = bar + 16;
-  auto kv_full = [&](int s) { return bar + 24 + 8u * s; };
-  auto kv_empty = [&](int s) { return bar + 40 + 8u * s; };
-  const uint32_t o_done = bar + 56;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 72);
+  const uint32_t s_full = bar + 8;    // MMA -> softmax: S(j) complete
+  const uint32_t s_free = bar + 16;   // softmax -> MMA: S(j) is in registers, the S columns may be overwritten
+  const uint32_t p_full = bar + 24;   // softmax -> MMA: P(j) written
+  const uint32_t p_free = bar + 32;   // MMA -> softmax: P V(j) retired (P columns and O are free again)
+  const uint32_t o_done = bar + 40;
+  auto k_full = [&](int s) { return bar + 48 + 8u * s; };
+  auto k_empty = [&](int s) { return bar + 72 + 8u * s; };
+  auto v_full = [&](int s) { return bar + 96 + 8u * s; };
+  auto v_empty = [&](int s) { return bar + 112 + 8u * s; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
@@ -71,10 +81,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if ((sbase & 1023u) != 0) __trap();  // swizzle-128B tiles need 1024-byte alignment
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
     mbar_init(p_full, 4);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+    mbar_init(p_free, 1);
+    for (int s = 0; s < K_STAGES; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+    }
+    for (int s = 0; s < V_STAGES; ++s) {
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
     }
     mbar_init(o_done, 1);
     mbar_fence_init();
@@ -88,7 +104,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tm_S = tmem;
-  const uint32_t tm_O = tmem + 128;
+  const uint32_t tm_P = tmem + 128;
+  const uint32_t tm_O = tmem + 192;
 
   // Warps 0 and 1 run warp-uniform loops and ONE elected lane issues the TMA / tcgen05 instructions, so that ptxas keeps
   // their operands in uniform registers (a `lane == 0` branch turns each issue into a vote/elect/R2UR loop).
@@ -102,12 +119,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     __syncwarp();
     for (int j = 0; j < p.nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1);
+      const int ks = j % K_STAGES, vs = j % V_STAGES;
+      mbar_wait(k_empty(ks), ((j / K_STAGES) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
-        tma_load_4d(sbase + SM_K + s * TILE_BYTES, &tmK, kv_full(s), h * AT_D, j * AT_BN, s_in, s_out);
-        tma_load_4d(sbase + SM_V + s * TILE_BYTES, &tmV, kv_full(s), h * AT_D, j * AT_BN, s_in, s_out);
+        mbar_expect_tx(k_full(ks), TILE_BYTES);
+        tma_load_4d(sbase + SM_K + ks * TILE_BYTES, &tmK, k_full(ks), h * AT_D, j * AT_BN, s_in, s_out);
+      }
+      __syncwarp();
+      mbar_wait(v_empty(vs), ((j / V_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(v_full(vs), TILE_BYTES);
+        tma_load_4d(sbase + SM_V + vs * TILE_BYTES, &tmV, v_full(vs), h * AT_D, j * AT_BN, s_in, s_out);
       }
       __syncwarp();
     }
@@ -115,38 +137,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S: A=Q K-major, B=K K-major
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // O: A=P K-major, B=V MN-major
     constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
-    auto issue_s = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(kv_full(s), (j >> 1) & 1);
+    const uint32_t q_lo = umma_desc_lo(sbase + SM_Q, 16);
+    auto issue_s = [&](int j) {   // S(j) = Q K(j)^T; releases the K stage and signals s_full when it retires
+      const int ks = j % K_STAGES;
+      mbar_wait(k_full(ks), (j / K_STAGES) & 1);
       tc_fence_after();
-      const uint32_t q_lo = umma_desc_lo(sbase + SM_Q, 16), k_lo = umma_desc_lo(sbase + SM_K + s * TILE_BYTES, 16);
+      const uint32_t k_lo = umma_desc_lo(sbase + SM_K + ks * TILE_BYTES, 16);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
           umma_ss_lohi(tm_S, q_lo + 2 * k, k_lo + 2 * k, desc_hi, idesc_s, k != 0);
         umma_commit(s_full);
+        umma_commit(k_empty(ks));
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0);
     issue_s(0);
     for (int j = 0; j < p.nblk; ++j) {
-      const int s = j & 1;
+      if (j + 1 < p.nblk) {
+        mbar_wait(s_free, j & 1);   // the softmax threads hold S(j) in registers
+        tc_fence_after();
+        issue_s(j + 1);             // runs while they compute the exponentials of block j
+      }
+      const int vs = j % V_STAGES;
       mbar_wait(p_full, j & 1);
+      mbar_wait(v_full(vs), (j / V_STAGES) & 1);
       tc_fence_after();
-      const uint32_t v_lo = umma_desc_lo(sbase + SM_V + s * TILE_BYTES, 16);
+      const uint32_t v_lo = umma_desc_lo(sbase + SM_V + vs * TILE_BYTES, 16);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)  // A = P from TMEM: 16 bf16 of K per step = 8 columns; V advances 16 rows
-          umma_ts_lohi(tm_O, tm_S + k * 8, v_lo + k * (2048 >> 4), desc_hi, idesc_o, (j | k) != 0);
-        umma_commit(kv_empty(s));
+          umma_ts_lohi(tm_O, tm_P + k * 8, v_lo + k * (2048 >> 4), desc_hi, idesc_o, (j | k) != 0);
+        umma_commit(v_empty(vs));
+        umma_commit(p_free);
+        if (j + 1 == p.nblk) umma_commit(o_done);
       }
       __syncwarp();
-      if (j + 1 < p.nblk) issue_s(j + 1);   // its commit (s_full) also covers the P V just issued
-      else {
-        if (elect_one()) umma_commit(o_done);
-        __syncwarp();
-      }
     }
   } else {
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
@@ -156,14 +183,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float c = p.scale_log2;
 
     for (int j = 0; j < p.nblk; ++j) {
-      mbar_wait(s_full, j & 1);   // S(j) is complete; in-order tensor pipe => P V(j-1) has retired too
+      mbar_wait(s_full, j & 1);   // S(j) is complete
       tc_fence_after();
       int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
       if (p.causal) {                // ... or lie above the diagonal for this query row
         const int lim = q0 + r + 1 - j * AT_BN;
         kvalid = lim < kvalid ? lim : kvalid;
       }
-      const bool full = kvalid >= AT_BN;
+      // warp-uniform: the tcgen05.ld/st below are .sync.aligned and must not sit in a divergent branch
+      const bool full = __all_sync(0xffffffffu, kvalid >= AT_BN);
       // the whole S row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait, and is
       // used for both the max and the exponentials (the first version re-read TMEM and stalled on 8 waits per block)
       uint32_t sv[AT_BN];
@@ -173,6 +201,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld_32x32(tm_S + lane_off + cc, chunk);
       }
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);   // S(j) now lives in registers: the MMA warp may start S(j+1)
       float mx;
       {
         float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
@@ -190,6 +221,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (i < kvalid) m0 = fmaxf(m0, __uint_as_float(sv[i]));
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      if (j > 0) {                // P V(j-1) must have retired before O is rescaled or P is overwritten
+        mbar_wait(p_free, (j - 1) & 1);
+        tc_fence_after();
       }
       // lazy running maximum: move it only when this block exceeds it by more than 8 (in log2 units)
       const float m_blk = mx * c;
@@ -211,28 +246,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-      // P = exp2(S*c - m) -> packed bf16 -> TMEM columns [cc/2, cc/2+16), i.e. over S columns already in registers
+      // P = exp2(S*c - m) -> packed bf16 -> TMEM columns [cc/2, cc/2+16), i.e. over S columns already in registers.
+      // Two straight-line copies: the unmasked one (all blocks but the last / the causal diagonal) carries no
+      // per-element compare+select — they were 2 of 7 instructions per element when the mask was predicated in.
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+      if (full) {
 #pragma unroll
-      for (int cc = 0; cc < AT_BN; cc += 32) {
-        uint32_t pk[16];
+        for (int cc = 0; cc < AT_BN; cc += 32) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 0]), c, -m_run));
-          float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
-          float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
-          float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
-          if (!full) {
+          for (int i = 0; i < 32; i += 4) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 0]), c, -m_run));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
+            ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+            pk[(i >> 1) + 0] = pack_bf16(e0, e1);
+            pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+          }
+          tmem_st_32x16(tm_P + lane_off + (cc >> 1), pk);
+        }
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < AT_BN; cc += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 0]), c, -m_run));
+            float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
+            float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
+            float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
             if (cc + i + 0 >= kvalid) e0 = 0.f;
             if (cc + i + 1 >= kvalid) e1 = 0.f;
             if (cc + i + 2 >= kvalid) e2 = 0.f;
             if (cc + i + 3 >= kvalid) e3 = 0.f;
+            ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+            pk[(i >> 1) + 0] = pack_bf16(e0, e1);
+            pk[(i >> 1) + 1] = pack_bf16(e2, e3);
           }
-          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
-          pk[(i >> 1) + 0] = pack_bf16(e0, e1);
-          pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+          tmem_st_32x16(tm_P + lane_off + (cc >> 1), pk);
         }
-        tmem_st_32x16(tm_S + lane_off + (cc >> 1), pk);
       }
       l_run += (ls0 + ls1) + (ls2 + ls3);
       tmem_st_wait();

@@ -28,14 +28,24 @@ class ControlledUnetModel(UNetModel):
     def forward_nhwc(self, x_nhwc: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
                      control: Optional[List[torch.Tensor]] = None, only_mid_control: bool = False):
         """x_nhwc: padded channels-last latent; control: 13 channels-last bf16 tensors (consumed from the end)."""
+        enc = self.encode_nhwc(x_nhwc, timesteps, context)
+        return self.decode_nhwc(enc, control, only_mid_control)
+
+    def encode_nhwc(self, x_nhwc: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor):
+        """Input blocks + middle block: the part of the UNet that does not depend on the ControlNet residuals
+        (controlnet.py:18-56 adds them only after the middle block), so ControlLDM can run it beside the ControlNet."""
         step = self._begin_step(timesteps, context)
-        control = None if control is None else list(control)
         hs = []
         h = x_nhwc
         for module in self.input_blocks:
             h = module(h, step)
             hs.append(h)
         h = self.middle_block(h, step)
+        return step, hs, h
+
+    def decode_nhwc(self, enc, control: Optional[List[torch.Tensor]] = None, only_mid_control: bool = False):
+        step, hs, h = enc
+        control = None if control is None else list(control)
         if control is not None:
             h = ops.add(h, control.pop())
         feats = []
