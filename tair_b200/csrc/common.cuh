@@ -362,8 +362,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  // bf16 -> fp32 is a 16-bit shift: one SHL + one LOP per pair (__bfloat1622float2 compiled to PRMT + 2 shifts)
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 // single MUFU.EX2 (exp2f without -use_fast_math adds range-fixup instructions)
 __device__ __forceinline__ float ex2_approx(float x) {

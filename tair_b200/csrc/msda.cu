@@ -13,6 +13,7 @@
 // The reference kernel uses one thread per output scalar, re-reading every location/weight/shape scalar
 // D times and doing the index arithmetic in int64 per tap.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/tair_b200.h"
 #include "common.cuh"
@@ -205,6 +206,121 @@ __global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p
   *reinterpret_cast<uint4*>(p.out + item * p.D + part * 8) = o;
 }
 
+
+// ---- L = 4 levels x P = 4 points (the TESTR configuration), slimmed down.  ncu on the general kernel above
+// (profiles/round1_summary.md): 4375 instructions per lane and item, 128 registers -> 16 resident warps per SM, issue
+// slots 45 % busy, L2 6 % busy: bound by its own instruction stream, not by the gather.  Here: 16-byte loads of the
+// offset / logit row, corner validity folded into the bilinear weights with clamped (always legal) addresses instead of
+// per-corner branches and zero fills, 32-bit offsets inside an image, <= 64 registers for 4 CTAs per SM. ----
+template <typename PJ> struct ProjVec;
+template <> struct ProjVec<float> {
+  static constexpr int PER = 4;  // values per 16-byte load
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+};
+template <> struct ProjVec<__nv_bfloat16> {
+  static constexpr int PER = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+};
+
+template <typename PJ>
+__global__ void __launch_bounds__(256, 4) msda_fused44_kernel(const MsdaFusedParams p) {
+  constexpr int LP = 16, PER = ProjVec<PJ>::PER;
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long item = gtid / p.lanes_per_item;
+  const int part = (int)(gtid - item * p.lanes_per_item);
+  if (item >= p.items) return;
+  const int m = (int)(item % p.M);
+  const long bq = item / p.M;
+  const int b = (int)(bq / p.Lq);
+  const int q = (int)(bq - (long)b * p.Lq);
+  const PJ* row = reinterpret_cast<const PJ*>(p.proj) + bq * p.ldp;
+  // softmax over the 16 logits of this (query, head)
+  float w[LP];
+#pragma unroll
+  for (int i = 0; i < LP / PER; ++i) {
+    float t[PER];
+    ProjVec<PJ>::load(row + (long)p.M * LP * 2 + m * LP + i * PER, t);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) w[i * PER + j] = t[j];
+  }
+  float mx = w[0];
+#pragma unroll
+  for (int i = 1; i < LP; ++i) mx = fmaxf(mx, w[i]);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LP; ++i) { w[i] = __expf(w[i] - mx); sum += w[i]; }
+  const float inv = 1.f / sum;
+  const float* refq = p.ref + (long)b * p.ref_batch_stride + (long)(q / p.q_per_ref) * 4 * p.ref_dim;
+  const __nv_bfloat16* vbase = p.value + ((long)b * p.S * p.M + m) * p.D + part * 8;
+  const int row_stride = p.M * p.D;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int H = (int)__ldg(p.shapes + 2 * l), W = (int)__ldg(p.shapes + 2 * l + 1);
+    const __nv_bfloat16* vl = vbase + (long)__ldg(p.starts + l) * row_stride;
+    const float fH = (float)H, fW = (float)W;
+    const uint8_t* vlb = reinterpret_cast<const uint8_t*>(vl);   // byte offsets inside a level fit 32 bits
+    const uint32_t rsb = (uint32_t)row_stride * 2u, wrs = (uint32_t)W * rsb;
+    const float rx = __ldg(refq + l * p.ref_dim), ry = __ldg(refq + l * p.ref_dim + 1);
+    float sx, sy;  // offset scale: 1/(W,H) for points, box_wh * 0.5 / P for boxes (ms_deform_attn.py:139-146)
+    if (p.ref_dim == 2) { sx = 1.f / fW; sy = 1.f / fH; }
+    else { sx = __ldg(refq + l * p.ref_dim + 2) * 0.125f; sy = __ldg(refq + l * p.ref_dim + 3) * 0.125f; }
+    float off[8];  // (x, y) of the 4 points of this level
+#pragma unroll
+    for (int i = 0; i < 8 / PER; ++i) {
+      float t[PER];
+      ProjVec<PJ>::load(row + m * LP * 2 + l * 8 + i * PER, t);
+#pragma unroll
+      for (int j = 0; j < PER; ++j) off[i * PER + j] = t[j];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float aw = w[l * 4 + s] * inv;
+      const float h_im = (ry + off[2 * s + 1] * sy) * fH - 0.5f;
+      const float w_im = (rx + off[2 * s] * sx) * fW - 0.5f;
+      const bool valid = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
+      const float fh = floorf(h_im), fw = floorf(w_im);
+      const int h_low = (int)fh, w_low = (int)fw;
+      const float lh = h_im - fh, lw = w_im - fw;
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      // a corner outside the map contributes zero: fold that into its weight and clamp its address into the map
+      const float wt = (valid && h_low >= 0) ? hh * aw : 0.f;
+      const float wb = (valid && h_low + 1 <= H - 1) ? lh * aw : 0.f;
+      const float wl = (w_low >= 0) ? hw : 0.f;
+      const float wr = (w_low + 1 <= W - 1) ? lw : 0.f;
+      const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_low + 1, 0), H - 1);
+      const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_low + 1, 0), W - 1);
+      const uint32_t r0 = (uint32_t)y0 * wrs, r1 = (uint32_t)y1 * wrs, c0 = (uint32_t)x0 * rsb, c1 = (uint32_t)x1 * rsb;
+      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c0)));
+      const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c1)));
+      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(vlb + (r1 + c0)));
+      const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(vlb + (r1 + c1)));
+      const float w1 = wt * wl, w2 = wt * wr, w3 = wb * wl, w4 = wb * wr;
+      const uint32_t a1[4] = {q1.x, q1.y, q1.z, q1.w}, a2[4] = {q2.x, q2.y, q2.z, q2.w};
+      const uint32_t a3[4] = {q3.x, q3.y, q3.z, q3.w}, a4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v1 = unpack_bf16(a1[i]), v2 = unpack_bf16(a2[i]), v3 = unpack_bf16(a3[i]), v4 = unpack_bf16(a4[i]);
+        acc[2 * i] = fmaf(w4, v4.x, fmaf(w3, v3.x, fmaf(w2, v2.x, fmaf(w1, v1.x, acc[2 * i]))));
+        acc[2 * i + 1] = fmaf(w4, v4.y, fmaf(w3, v3.y, fmaf(w2, v2.y, fmaf(w1, v1.y, acc[2 * i + 1]))));
+      }
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(p.out + item * p.D + part * 8) = o;
+}
+
 }  // namespace
 }  // namespace tair
 
@@ -265,7 +381,13 @@ extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes,
   const long grid = (threads_total + 255) / 256;
   TAIR_REQUIRE(grid < (1l << 31), "msda_fused: problem too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (L == 4 && P == 4) {
+  const size_t pj = proj_bf16 ? 2 : 4;
+  const bool fast44 = L == 4 && P == 4 && (reinterpret_cast<uintptr_t>(proj) % 16) == 0 && (ldp * pj) % 16 == 0 &&
+                      ((size_t)M * 32 * pj) % 16 == 0 && (long)S * M * D < (1l << 30) && !getenv("TAIR_MSDA_GENERIC");
+  if (fast44) {
+    if (proj_bf16) msda_fused44_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
+    else msda_fused44_kernel<float><<<(unsigned)grid, 256, 0, st>>>(p);
+  } else if (L == 4 && P == 4) {
     if (proj_bf16) msda_fused_kernel<4, 4, __nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
     else msda_fused_kernel<4, 4, float><<<(unsigned)grid, 256, 0, st>>>(p);
   } else {
