@@ -44,6 +44,9 @@ struct AttnParams {
   int H, Lq, Lk;
   int n_inner;       // sequences are indexed (outer, inner); plain batched attention has n_inner == 1
   int causal;        // key j attends only to queries i >= j (OpenCLIP text transformer)
+  int group;         // > 0: block-diagonal mode — the rows are back-to-back sequences of `group` tokens, a tile packs
+                     // tile_rows / group of them and every row only sees the keys of its own sequence
+  int tile_rows;     // query rows per CTA: 128, or (128 / group) * group in block-diagonal mode
   int q_tiles, nblk;
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* o;
@@ -75,7 +78,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = bh % p.H;
   const int seq = bh / p.H;
   const int s_in = seq % p.n_inner, s_out = seq / p.n_inner;
-  const int q0 = qt * AT_BM;
+  const int q0 = qt * p.tile_rows;
+  const int kv0 = p.group > 0 ? q0 : 0;   // block-diagonal mode: the only key block is the tile's own rows
 
   if (threadIdx.x == 0) {
     if ((sbase & 1023u) != 0) __trap();  // swizzle-128B tiles need 1024-byte alignment
@@ -123,13 +127,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(k_empty(ks), ((j / K_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(k_full(ks), TILE_BYTES);
-        tma_load_4d(sbase + SM_K + ks * TILE_BYTES, &tmK, k_full(ks), h * AT_D, j * AT_BN, s_in, s_out);
+        tma_load_4d(sbase + SM_K + ks * TILE_BYTES, &tmK, k_full(ks), h * AT_D, kv0 + j * AT_BN, s_in, s_out);
       }
       __syncwarp();
       mbar_wait(v_empty(vs), ((j / V_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(v_full(vs), TILE_BYTES);
-        tma_load_4d(sbase + SM_V + vs * TILE_BYTES, &tmV, v_full(vs), h * AT_D, j * AT_BN, s_in, s_out);
+        tma_load_4d(sbase + SM_V + vs * TILE_BYTES, &tmV, v_full(vs), h * AT_D, kv0 + j * AT_BN, s_in, s_out);
       }
       __syncwarp();
     }
@@ -185,13 +189,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int j = 0; j < p.nblk; ++j) {
       mbar_wait(s_full, j & 1);   // S(j) is complete
       tc_fence_after();
-      int kvalid = p.Lk - j * AT_BN;  // columns >= kvalid are padding (only in the last block)
-      if (p.causal) {                // ... or lie above the diagonal for this query row
+      int klo = 0;                           // this row sees key columns [klo, kvalid) of the block
+      int kvalid = p.Lk - kv0 - j * AT_BN;   // columns >= kvalid are padding (only in the last block)
+      if (p.causal) {                        // ... or lie above the diagonal for this query row
         const int lim = q0 + r + 1 - j * AT_BN;
         kvalid = lim < kvalid ? lim : kvalid;
       }
+      if (p.group > 0) {                     // ... or belong to another sequence of the packed tile
+        klo = (r / p.group) * p.group;
+        const int hi = klo + p.group;
+        if (r >= p.tile_rows || klo >= kvalid) { klo = 0; kvalid = 1; }   // unused row: keep the arithmetic finite
+        else kvalid = hi < kvalid ? hi : kvalid;
+      }
       // warp-uniform: the tcgen05.ld/st below are .sync.aligned and must not sit in a divergent branch
-      const bool full = __all_sync(0xffffffffu, kvalid >= AT_BN);
+      const bool full = __all_sync(0xffffffffu, klo == 0 && kvalid >= AT_BN);
       // the whole S row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait, and is
       // used for both the max and the exponentials (the first version re-read TMEM and stalled on 8 waits per block)
       uint32_t sv[AT_BN];
@@ -218,7 +229,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         } else {
 #pragma unroll
           for (int i = 0; i < AT_BN; ++i)
-            if (i < kvalid) m0 = fmaxf(m0, __uint_as_float(sv[i]));
+            if (i >= klo && i < kvalid) m0 = fmaxf(m0, __uint_as_float(sv[i]));
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
@@ -276,10 +287,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
             float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
             float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
-            if (cc + i + 0 >= kvalid) e0 = 0.f;
-            if (cc + i + 1 >= kvalid) e1 = 0.f;
-            if (cc + i + 2 >= kvalid) e2 = 0.f;
-            if (cc + i + 3 >= kvalid) e3 = 0.f;
+            if (cc + i + 0 >= kvalid || cc + i + 0 < klo) e0 = 0.f;
+            if (cc + i + 1 >= kvalid || cc + i + 1 < klo) e1 = 0.f;
+            if (cc + i + 2 >= kvalid || cc + i + 2 < klo) e2 = 0.f;
+            if (cc + i + 3 >= kvalid || cc + i + 3 < klo) e3 = 0.f;
             ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
             pk[(i >> 1) + 0] = pack_bf16(e0, e1);
             pk[(i >> 1) + 1] = pack_bf16(e2, e3);
@@ -303,7 +314,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       uint32_t ov[32];
       tmem_ld_32x32(tm_O + lane_off + half * 32, ov);
       tmem_ld_wait();
-      if (q < p.Lq) {
+      if (q < p.Lq && r < p.tile_rows) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
@@ -342,12 +353,14 @@ int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int6
 int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                      int64_t ldo, int H, int Lq, int Lk, int64_t n_outer, int n_inner, int64_t q_outer, int64_t q_inner,
                      int64_t q_tok, int64_t kv_outer, int64_t kv_inner, int64_t kv_tok, float scale, int causal,
-                     void* stream) {
+                     void* stream, int group = 0) {
   AttnParams p{};
   p.causal = causal;
+  p.group = group;
+  p.tile_rows = group > 0 ? (AT_BM / group) * group : AT_BM;
   p.H = H; p.Lq = Lq; p.Lk = Lk; p.n_inner = n_inner;
-  p.q_tiles = (Lq + AT_BM - 1) / AT_BM;
-  p.nblk = (Lk + AT_BN - 1) / AT_BN;
+  p.q_tiles = (Lq + p.tile_rows - 1) / p.tile_rows;
+  p.nblk = group > 0 ? 1 : (Lk + AT_BN - 1) / AT_BN;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.ldo = ldo;
@@ -398,6 +411,12 @@ extern "C" int tair_attention_seq_bf16(const void* q, const void* k, const void*
   TAIR_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ld >= H * 64 && ldo >= H * 64, "attention_seq: bad row strides");
   for (const void* ptr : {q, k, v, (const void*)o})
     TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention_seq: pointers must be 16-byte aligned");
+  // Short sequences stored back to back (the TESTR decoder's intra-group attention: 100*B sequences of 16 / 25 points,
+  // deformable_transformer.py:454-466) would each occupy a 128-row tensor-core tile for 16-25 useful rows; they are
+  // packed 128/L to a tile instead and attended block-diagonally.
+  if (n_inner == 1 && tok_stride == 1 && outer_stride == L && L <= 64 && n_outer * L < (1ll << 31))
+    return launch_attention(q, ld, k, ld, v, ld, o, ldo, H, (int)(n_outer * L), (int)(n_outer * L), 1, 1, 0, 0, 1, 0, 0, 1,
+                            scale, 0, stream, L);
   return launch_attention(q, ld, k, ld, v, ld, o, ldo, H, L, L, n_outer, n_inner, outer_stride, inner_stride,
                           tok_stride, outer_stride, inner_stride, tok_stride, scale, 0, stream);
 }

@@ -404,7 +404,8 @@ def msda_fused(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_in
         raise TairError("msda_fused: inconsistent shapes")
     out = torch.empty((B * Lq, M * D), device=value.device, dtype=BF16)
     stride = 0 if ref_shared else n_ref * n_levels * ref_dim
-    with _timed("msda", 2.0 * out.numel() + 2.0 * value.numel() + 4.0 * p2.shape[0] * M * n_levels * n_points * 3):
+    with _timed("msda", 2.0 * out.numel() + 2.0 * value.numel() + 4.0 * p2.shape[0] * M * n_levels * n_points * 3,
+                (B, Lq, M, n_levels, n_points)):
         rc = _lib.lib().tair_msda_fused(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                                         p2.data_ptr(), ldp, int(proj.dtype == BF16), ref.data_ptr(), ref_dim, stride,
                                         q_per_ref, out.data_ptr(),
@@ -443,7 +444,7 @@ def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_in
         out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
     o2, ldo = _rows(out, "out")
     base = q2.data_ptr()
-    with _timed("attention_seq", 4.0 * n_outer * n_inner * n_heads * L * L * 64):
+    with _timed("attention_seq", 4.0 * n_outer * n_inner * n_heads * L * L * 64, (n_outer, n_inner, n_heads, L)):
         rc = _lib.lib().tair_attention_seq_bf16(base, base + 2 * E, base + 4 * E, ld, o2.data_ptr(), ldo, n_heads, L,
                                                 n_outer, n_inner, outer_stride, inner_stride, tok_stride, float(scale),
                                                 _stream())

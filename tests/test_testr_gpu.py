@@ -85,7 +85,9 @@ def test_mha_small_vs_torch(cuda_lib, L, n_outer, n_inner):
     assert rel(out, ref.reshape(rows, E)) < 1e-2
 
 
-@pytest.mark.parametrize("L,n_outer,n_inner", [(16, 200, 1), (25, 100, 1), (100, 2, 16), (100, 2, 25)])
+@pytest.mark.parametrize("L,n_outer,n_inner", [(16, 200, 1), (25, 100, 1), (100, 2, 16), (100, 2, 25),
+                                               # packed block-diagonal tiles: ragged last tile, odd group sizes
+                                               (25, 1603, 1), (16, 37, 1), (7, 1000, 1), (64, 5, 1), (1, 300, 1), (65, 4, 1)])
 def test_attention_seq_padded_heads_vs_torch(cuda_lib, L, n_outer, n_inner):
     """tcgen05 attention on strided short sequences with 32-wide heads zero-padded to 64-column slots."""
     import torch.nn.functional as F

@@ -18,10 +18,7 @@ ops.set_timer(None); torch.cuda.synchronize()
 print("total eager ms", a.elapsed_time(b))
 for k, v in sorted(t.summary().items(), key=lambda kv: -kv[1]["ms"]):
     print(f"{k:12s} launches={v['launches']:4d} ms={v['ms']:.3f}")
-# per-shape GEMM list
-import collections
-agg = collections.defaultdict(lambda: [0, 0.0])
-for (ea, eb, w) in t.records.get("gemm", []):
-    agg[int(w)][0] += 1; agg[int(w)][1] += ea.elapsed_time(eb)
-for w, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
-    print(f"gemm flops={w/1e9:8.2f}G n={n:3d} ms={ms:.3f} -> {w*n/ms/1e9:.0f} TFLOP/s")
+rows = sorted(t.by_shape().items(), key=lambda kv: -kv[1]["ms"])
+for (fam, tag), v in rows[:30]:
+    unit = "GB/s" if fam in ("groupnorm", "layernorm", "msda") else "TF/s"
+    print(f"{fam:13s} {str(tag):34s} x{v['launches']:3d} {v['ms']:7.3f} ms  {v['work'] / v['ms'] / 1e9:8.0f} {unit} ({v['ms'] / v['launches'] * 1e3:.1f} us each)")
