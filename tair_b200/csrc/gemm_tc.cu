@@ -205,7 +205,7 @@ template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC64,
                                                   const CUtensorMap* tmC32, int m0q, int tn, int half, int lane,
                                                   uint32_t taddr, uint8_t* stg, uint32_t tempty_bar_addr,
-                                                  bool remote_arrive = false) {
+                                                  bool remote_arrive, uint32_t tfull_bar_addr, uint32_t tfull_phase) {
   const tair_epilogue& e = p.epi;
   constexpr bool GEGLU = (ACT == TAIR_ACT_GEGLU);
   constexpr int NT = GEGLU ? BN / 2 : BN;      // output columns produced by this tile
@@ -226,6 +226,21 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     if (remote_arrive) mbar_arrive_cluster(tempty_bar_addr);
     else mbar_arrive(tempty_bar_addr);
   };
+  // Residual rows are prefetched one 32-column group ahead, the first group even before the accumulator is complete:
+  // a thread-per-row read issued at its point of use exposes a full L2/HBM round trip per group (the K=320
+  // projections with a residual ran 50 us against 23 us without one; 42 us with the prefetch).  A variant that also
+  // made the loads row-contiguous through the staging buffer needed 8 more live 16-byte registers and spilled.
+  uint4 rpre[4] = {};
+  auto res_vec_ok = [&](int n) { return resp != nullptr && p.vec_res && n + 32 <= n_total; };
+  auto prefetch = [&](int n) {
+    if (res_vec_ok(n)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rpre[q] = __ldg(reinterpret_cast<const uint4*>(resp + n + q * 8));
+    }
+  };
+  if (half < NSUB) prefetch(n_out0 + half * 64);
+  mbar_wait(tfull_bar_addr, tfull_phase);
+  tc_fence_after();
   if (half >= NSUB) {  // nothing to drain for this warp (narrow tiles): just release the accumulator
     tc_fence_before();
     __syncwarp();
@@ -242,6 +257,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     for (int g = 0; g < ncol; g += 32) {
       float v[32];
       const int n = n_out0 + c0 + g;                   // first output column of this 32-wide group
+      uint4 rcur[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rcur[q] = rpre[q];
+      {
+        const int n_next = (g + 32 < ncol) ? n + 32 : n_out0 + (s + 2) * 64;   // next group of this warp, if any
+        if ((g + 32 < ncol) || (s + 2 < NSUB)) prefetch(n_next);
+      }
       if constexpr (GEGLU) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {               // 16 columns at a time keeps register pressure down
@@ -293,10 +315,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         }
       }
       if (resp != nullptr) {
-        if (p.vec_res && n + 32 <= n_total) {
+        if (res_vec_ok(n)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(resp + n + q * 8));
+            const uint4 w = rcur[q];
             const float2 b0 = unpack_bf16(w.x), b1 = unpack_bf16(w.y), b2 = unpack_bf16(w.z), b3 = unpack_bf16(w.w);
             v[q * 8 + 0] += b0.x; v[q * 8 + 1] += b0.y; v[q * 8 + 2] += b1.x; v[q * 8 + 3] += b1.y;
             v[q * 8 + 4] += b2.x; v[q * 8 + 5] += b2.y; v[q * 8 + 6] += b3.x; v[q * 8 + 7] += b3.y;
@@ -480,8 +502,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int m0q = tm * BM + quad * 32;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+      if (!p.tma_store || (p.dbg & 2)) {   // the TMA-store epilogue waits itself, after its first residual prefetch
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       if ((p.dbg & 2) || (!p.tma_store && half == 1)) {
         tc_fence_before();
@@ -489,11 +513,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       } else if (p.tma_store) {
         switch (e.act) {
-          case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
-          case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
-          case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
-          case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
-          default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc)); break;
+          case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
+          case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
+          case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
+          case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
+          default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
         }
       } else {
         // fp32 / unaligned outputs (small heads): direct thread-per-row stores by the first four epilogue warps
@@ -689,8 +713,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int tm2 = tile / p.tiles_n, tn = tile - tm2 * p.tiles_n;
       const int m0q = (tm2 * 2 + (int)rank) * BM + quad * 32;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+      if (p.dbg & 2) {   // otherwise the epilogue waits itself, after its first residual prefetch
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const uint32_t tempty_leader = leader ? tempty_bar(acc) : mapa_shared(tempty_bar(acc), 0);
       if (p.dbg & 2) {
@@ -699,11 +725,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) { if (leader) mbar_arrive(tempty_leader); else mbar_arrive_cluster(tempty_leader); }
       } else
       switch (e.act) {
-        case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
-        case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
-        case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
-        case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
-        default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader); break;
+        case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
+        case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
+        case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
+        case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
+        default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -8,7 +8,7 @@ python tools/ncu_step.py $B > $OUT/${TAG}_plain.log 2>&1 || { echo "plain run fa
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/${TAG}_launches.csv python tools/ncu_step.py $B > $OUT/${TAG}_list.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:"gemm_tc_kernel|attn_tc_kernel|gn_apply|gn_stats|layernorm" -c 24 -f -o /tmp/${TAG}_prof \
+    -k regex:"gemm_tc_kernel|attn_tc_kernel|gn_apply|gn_stats|layernorm" -c 40 -f -o /tmp/${TAG}_prof \
     python tools/ncu_step.py $B > $OUT/${TAG}_full.log 2>&1
 ncu -i /tmp/${TAG}_prof.ncu-rep --page raw --csv > $OUT/${TAG}_prof_raw.csv 2>/dev/null
 ls -la /tmp/${TAG}_prof.ncu-rep
