@@ -75,6 +75,12 @@ typedef struct tair_epilogue {
   int64_t ldg;
   int32_t rows_per_group;
   int32_t reserved;
+  void* workspace;         /* optional scratch (16-byte aligned, private to the stream) or NULL.  When given and large
+                              enough (3 * M * N * 4 bytes), tair_conv3x3_bf16 computes layers whose OUTPUT image is at
+                              most 8x8 with K >= 4096 as a 3-way split-K: fp32 partial tiles in the workspace, then
+                              a fixed-order reduction + epilogue kernel.  The split depends on the layer geometry
+                              only, never on the batch, so results stay batch-independent.                     */
+  int64_t workspace_bytes;
 } tair_epilogue;
 
 /* out = epilogue(A[M,K] * W[N,K]^T).  A, W bf16, K contiguous; lda/ldw in elements

@@ -36,6 +36,8 @@ class Epilogue(C.Structure):
         ("ldg", C.c_int64),
         ("rows_per_group", C.c_int32),
         ("reserved", C.c_int32),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
     ]
 
 

@@ -50,6 +50,8 @@ struct GemmParams {
   int Ho, Wo, stride, pad;
   int vec_out, vec_res, vec_rg;
   int tma_store;  // bf16 output eligible for the TMA-store epilogue
+  int splits;      // split-K: each tile is computed by `splits` CTAs over kb_split k-blocks each; fp32 partials go to
+  int kb_split;    // rows [split*M, split*M + M) of the (workspace) output, a second kernel reduces + applies the epilogue
   int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the epilogue body, 4 / 8 load B / A only for the first tile
   tair_epilogue epi;
 };
@@ -399,7 +401,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;   // work items: (tile, K split)
+  const int mn_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
     // The whole warp runs the loop and ONE elected lane issues: with warp-uniform control flow ptxas keeps the TMA /
@@ -411,7 +414,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles && !(p.dbg & 32); tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_tiles && !(p.dbg & 32); work += gridDim.x) {
+      const int split = work / mn_tiles, tile = work - split * mn_tiles;
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
       int img = 0, ho0 = 0, wo0 = 0;
@@ -422,10 +426,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ho0 = rem / p.Wo;
         wo0 = rem - ho0 * p.Wo;
       }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int kb0 = split * p.kb_split;
+      const int kb1 = (kb0 + p.kb_split < p.num_kb) ? kb0 + p.kb_split : p.num_kb;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
-        const bool skip_b = (p.dbg & 4) && tile != (int)blockIdx.x;
-        const bool skip_a = (p.dbg & 8) && tile != (int)blockIdx.x;
+        const bool skip_b = (p.dbg & 4) && work != (int)blockIdx.x;
+        const bool skip_a = (p.dbg & 8) && work != (int)blockIdx.x;
         const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
         const uint32_t b_dst = a_dst + A_BYTES;
         int c0 = kb * BK, c1 = m0, c2 = 0, c3 = 0;
@@ -462,11 +468,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int kb0 = (work / mn_tiles) * p.kb_split;
+      const int kb1 = (kb0 + p.kb_split < p.num_kb) ? kb0 + p.kb_split : p.num_kb;
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (!(p.dbg & 32)) {  // dbg 32 (probe): back-to-back MMA issue without the smem pipeline handshake
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -474,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
         const uint32_t b_lo = a_lo + (A_BYTES >> 4);
         if (elect_one()) {
-          umma_ss_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != 0);
+          umma_ss_lohi(d_tmem, a_lo, b_lo, desc_hi, idesc, kb != kb0);
 #pragma unroll
           for (int k = 1; k < BK / 16; ++k)  // +32 bytes along K inside the 128-byte swizzle atom = +2 in the address field
             umma_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
@@ -499,7 +507,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      const int split = work / mn_tiles, tile = work - split * mn_tiles;
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int m0q = tm * BM + quad * 32;
       if (!p.tma_store || (p.dbg & 2)) {   // the TMA-store epilogue waits itself, after its first residual prefetch
@@ -521,8 +530,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         // fp32 / unaligned outputs (small heads): direct thread-per-row stores by the first four epilogue warps
-        const int m = m0q + lane;
-        const bool row_ok = m < p.M;
+        const bool row_ok = m0q + lane < p.M;
+        const int m = m0q + lane + split * p.M;   // split-K partials: split s owns rows [s*M, s*M + M) of the workspace
         switch (e.act) {
           case TAIR_ACT_GEGLU: epilogue_tile<BN, TAIR_ACT_GEGLU>(p, m, tn, row_ok, taddr); break;
           case TAIR_ACT_GELU: epilogue_tile<BN, TAIR_ACT_GELU>(p, m, tn, row_ok, taddr); break;
@@ -772,7 +781,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
                                    (int)Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC64, tmC32, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -891,6 +900,73 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Split-K for small-M / deep-K problems (the 8x8 levels: M = 64 * batch pixels, K = 9 * 1280 ... 9 * 2560).  With
+// 128-row tiles such a problem has only 64-80 tiles, every active SM is pinned at its ~55 B/clk operand ingest (ncu:
+// 622 cycles per k-block on 80 SMs, tensor pipe 44 %) and half the chip idles.  `splits` CTAs share a tile's K range,
+// write fp32 partial tiles to a workspace, and a second small kernel sums them in a FIXED order (deterministic) and
+// applies the epilogue.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, const tair_epilogue e) {
+  const int64_t idx4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread = 4 consecutive columns
+  const int n4 = N >> 2;
+  if (idx4 >= (int64_t)M * n4) return;
+  const int m = (int)(idx4 / n4), n = (int)(idx4 - (int64_t)m * n4) * 4;
+  float4 acc = *reinterpret_cast<const float4*>(ws + (int64_t)m * N + n);
+  for (int s = 1; s < splits; ++s) {
+    const float4 t = *reinterpret_cast<const float4*>(ws + ((int64_t)s * M + m) * N + n);
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float* rg = e.rowgroup == nullptr ? nullptr
+                    : e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (e.bias != nullptr) v[j] += __ldg(e.bias + n + j);
+    if (rg != nullptr) v[j] += __ldg(rg + n + j);
+    switch (e.act) {
+      case TAIR_ACT_GELU: v[j] = gelu_f(v[j]); break;
+      case TAIR_ACT_SILU: v[j] = silu_f(v[j]); break;
+      case TAIR_ACT_RELU: v[j] = fmaxf(v[j], 0.f); break;
+      default: break;
+    }
+    if (e.residual != nullptr)
+      v[j] += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.residual)[(int64_t)m * e.ldr + n + j]);
+  }
+  if (e.out_fp32) {
+    float* o = reinterpret_cast<float*>(e.out) + (int64_t)m * e.ldc + n;
+    for (int j = 0; j < 4; ++j) o[j] = v[j];
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + (int64_t)m * e.ldc + n;
+    for (int j = 0; j < 4; ++j) o[j] = __float2bfloat16(v[j]);
+  }
+}
+
+bool legal_splitk(const GemmParams& p, int act, int bn, int splits) {
+  if (act == TAIR_ACT_GEGLU || p.N % 4 != 0 || splits < 2) return false;
+  const long tiles = (long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn);
+  return tiles * splits <= num_sms() && p.num_kb / splits >= 8;
+}
+
+int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn, bool two, cudaStream_t st);
+
+// `ws` holds splits * M * N floats
+int dispatch_splitk(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn, int splits,
+                    cudaStream_t st, void* ws) {
+  GemmParams q = p;
+  q.splits = splits;
+  q.kb_split = (p.num_kb + splits - 1) / splits;
+  q.epi = tair_epilogue{};
+  q.epi.out = ws; q.epi.ldc = p.N; q.epi.out_fp32 = 1;
+  q.vec_out = 1; q.vec_res = 0; q.vec_rg = 0;
+  int rc = dispatch(tmA, W, ldw, q, bn, false, st);
+  if (rc) return rc;
+  const int64_t n4 = (int64_t)p.M * (p.N / 4);
+  splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws), splits, p.M, p.N, p.epi);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("splitk_reduce_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Tile autotuner.  Which (BN, 1-CTA / 2-CTA pair) is fastest depends on wave quantisation, on the K depth and on how
 // many SMs share the L2 -> SM operand path; no closed-form rule got within 25 % on every shape of the UNet
 // (tools/bn_sweep.py), so the first call for a problem shape times every legal candidate on the caller's stream
@@ -904,7 +980,7 @@ struct TuneKey {
     return std::memcmp(this, &o, sizeof(TuneKey)) < 0;
   }
 };
-struct TuneChoice { int bn; bool two; };
+struct TuneChoice { int bn; bool two; int splits; };
 
 std::mutex g_tune_mu;
 std::map<TuneKey, TuneChoice> g_tuned;
@@ -929,6 +1005,12 @@ int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const
   p.tiles_m = (p.M + BM - 1) / BM;
   if (const char* f = getenv("TAIR_GEMM_BN")) {  // bring-up probe only
     const int bn = atoi(f);
+    if (const char* sp = getenv("TAIR_GEMM_SPLITS")) {   // probe: needs a caller workspace
+      const int splits = atoi(sp);
+      if (legal_splitk(p, act, bn, splits) && p.epi.workspace != nullptr &&
+          (size_t)p.epi.workspace_bytes >= (size_t)splits * p.M * p.N * sizeof(float))
+        return dispatch_splitk(tmA, W, ldw, p, bn, splits, st, p.epi.workspace);
+    }
     return dispatch(tmA, W, ldw, p, bn, use_2cta(p, bn), st);
   }
   const int heur = pick_bn(p.M, p.N, p.num_kb, act);
@@ -937,8 +1019,8 @@ int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const
   const int n_out = act == TAIR_ACT_GEGLU ? p.N / 2 : p.N;
   const size_t out_bytes = ((size_t)(p.M - 1) * p.epi.ldc + n_out) * esz;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  const bool tunable = autotune_enabled() && act != TAIR_ACT_GEGLU && p.dbg == 0 &&
-                       cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone &&
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+  const bool tunable = autotune_enabled() && act != TAIR_ACT_GEGLU && p.dbg == 0 && cap == cudaStreamCaptureStatusNone &&
                        !overlaps(p.epi.out, out_bytes, A, in_bytes) &&
                        !overlaps(p.epi.out, out_bytes, p.epi.residual, p.epi.residual ? ((size_t)(p.M - 1) * p.epi.ldr + n_out) * 2 : 0);
   TuneKey key;
@@ -958,7 +1040,7 @@ int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const
   TAIR_CUDA(cudaEventCreate(&e0));
   TAIR_CUDA(cudaEventCreate(&e1));
   const int64_t launches_before = g_launch_count.load();
-  TuneChoice best{heur, use_2cta(p, heur)};
+  TuneChoice best{heur, use_2cta(p, heur), 1};
   float best_ms = -1.f;
   int rc = TAIR_OK;
   for (int i = 0; i < 7 && rc == TAIR_OK; ++i) {
@@ -973,7 +1055,7 @@ int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const
       if (cudaEventSynchronize(e1) != cudaSuccess) { rc = check_launch("gemm autotune"); if (rc == TAIR_OK) rc = TAIR_ERR_CUDA; break; }
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
-      if (best_ms < 0.f || ms < best_ms) { best_ms = ms; best = TuneChoice{bn, two != 0}; }
+      if (best_ms < 0.f || ms < best_ms) { best_ms = ms; best = TuneChoice{bn, two != 0, 1}; }
     }
   }
   cudaEventDestroy(e0);
@@ -1007,6 +1089,7 @@ extern "C" int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.num_kb = (K + BK - 1) / BK;
+  p.splits = 1; p.kb_split = p.num_kb;
   p.conv = 0;
   const int act = epi ? epi->act : 0;
   const int n_out = (act == TAIR_ACT_GEGLU) ? N / 2 : N;
@@ -1047,6 +1130,7 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   GemmParams p{};
   p.M = B * Ho * Wo; p.N = Cout; p.K = 9 * Cin;
   p.num_kb = 9 * (Cin / BK);
+  p.splits = 1; p.kb_split = p.num_kb;
   p.conv = 1; p.kb_per_tap = Cin / BK;
   p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.pad = pad;
   const int act = epi ? epi->act : 0;
@@ -1060,5 +1144,14 @@ extern "C" int tair_conv3x3_bf16(const void* x, const void* w, int32_t B, int32_
   const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   rc = make_tmap_bf16(&tmA, x, 4, dimsA, strA, boxA, es, true);
   if (rc) return rc;
+  // Deep-K layers on the 8x8 level (<= 64 output pixels per image): 3-way split-K when the caller lends a workspace.
+  // The rule looks at the layer geometry only, so a tile's numbers do not depend on the batch it is processed in.
+  constexpr int SPLITS = 3;
+  if (Ho * Wo <= 64 && p.num_kb >= 64 && Cout % 4 == 0 && p.dbg == 0 && !getenv("TAIR_GEMM_BN") && p.epi.workspace != nullptr &&
+      (reinterpret_cast<uintptr_t>(p.epi.workspace) % 16) == 0 &&
+      (size_t)p.epi.workspace_bytes >= (size_t)SPLITS * p.M * p.N * sizeof(float)) {
+    const int bn = Cout % 256 == 0 ? 256 : (Cout % 160 == 0 ? 160 : 128);
+    return dispatch_splitk(tmA, w, (int64_t)9 * Cin, p, bn, SPLITS, static_cast<cudaStream_t>(stream), p.epi.workspace);
+  }
   return tuned_dispatch(tmA, x, (size_t)B * H * W * Cin * 2, w, (int64_t)9 * Cin, p, act, static_cast<cudaStream_t>(stream));
 }

@@ -149,6 +149,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup
     return out
 
 
+_sk_ws: dict = {}
+
+
+def _splitk_workspace(device, need: int) -> torch.Tensor:
+    """Scratch for split-K partial sums, one buffer per (device, stream) like the GroupNorm workspace: two streams of one
+    process (ControlNet beside the UNet encoder) may run split-K convolutions at the same time."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _sk_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 16 << 20), device=device, dtype=torch.uint8)
+        _sk_ws[key] = ws
+    return ws
+
+
 def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad: int = 1, bias=None, residual=None,
             rowgroup=None, rows_per_group=0, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
             out_dtype=BF16) -> torch.Tensor:
@@ -168,6 +182,11 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad: int = 1, 
     o2 = out.view(M, -1) if out.dim() == 4 else out
     r2 = residual.view(M, -1) if (residual is not None and residual.dim() == 4) else residual
     e = _make_epilogue(o2, M, Cout, bias, r2, rowgroup, rows_per_group, act)
+    if Ho * Wo <= 64 and Cin >= 448:
+        # deep-K layer on an (at most) 8x8 map: lend the library a per-stream scratch so it can run a 3-way split-K
+        # (too few 128-row tiles to fill the SMs otherwise); see tair_epilogue.workspace in include/tair_b200.h
+        ws = _splitk_workspace(x.device, 3 * M * Cout * 4)
+        e.workspace, e.workspace_bytes = ws.data_ptr(), ws.numel()
     with _timed("conv3x3", 2.0 * M * Cout * 9 * Cin, (B, H, W, Cin, Cout, stride)):
         rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, pad, C.byref(e), _stream())
     _lib.check(rc, "tair_conv3x3_bf16")
