@@ -6,9 +6,12 @@ they are sharded round-robin over ranks (``tiles.shard_tiles``), batched ``tile_
 CUDA-graph step, decoded, reassembled with ONE all-gather and blended by one kernel.  Noise is keyed by the GLOBAL
 tile index, so the restored image is bit-identical for every world size and batch size.
 
-The stages that are not yet on our kernels (SwinIR cleaner, VAE, CLIP: SURVEY.md §8f) are passed in as callables:
-    cond_fn(lq)   : (b,3,512,512) fp32 in [0,1]  -> {"c_txt": (b,77,1024), "c_img": (b,4,64,64)}
-    decode_fn(z)  : (b,4,64,64) latent           -> (b,3,512,512) fp32 in [0,1]
+Stages around the denoising loop (val_patches.py:318-370):
+    cleaner(lq)   : (b,3,512,512) in [0,1] -> cleaned image.  SwinIR is not on our kernels yet:
+                    pass the torch module (or any callable); default = identity.
+    cond_fn(lq)   : -> {"c_txt": (b,77,1024), "c_img": (b,4,64,64)}.  Default: ``cldm.prepare_condition(cleaner(lq), [""]*b)``
+                    i.e. the kernel VAE encoder + the kernel OpenCLIP text encoder of ``cldm`` (cldm.py:143-158).
+    decode_fn(z)  : (b,4,64,64) latent -> (b,3,512,512) in [0,1].  Default: ``(cldm.vae_decode(z) + 1) / 2`` (kernel VAE).
 """
 from __future__ import annotations
 
@@ -45,12 +48,21 @@ class _TileNoise:
 
 
 @torch.no_grad()
-def restore_image(lq: np.ndarray, cldm, sampler, *, cond_fn: Callable, decode_fn: Callable, ts_model=None,
+def restore_image(lq: np.ndarray, cldm, sampler, *, cond_fn: Optional[Callable] = None,
+                  decode_fn: Optional[Callable] = None, cleaner: Optional[Callable] = None, ts_model=None,
                   steps: int = 50, tile_batch: int = 16, cfg_scale: float = 1.0, uncond_fn: Optional[Callable] = None,
                   seed: int = 25, group=None, use_cuda_graph: bool = True, cfg=None) -> torch.Tensor:
     """lq: (H,W,3) uint8 low-quality image -> (1,3,4H,4W) restored image on every rank."""
     import torch.distributed as dist
     dev = next(cldm.parameters()).device
+    if cond_fn is None:
+        if cldm.vae is None or cldm.clip is None:
+            raise RuntimeError("restore_image: pass cond_fn, or build ControlLDM with vae_cfg and clip_cfg")
+        cond_fn = lambda x: cldm.prepare_condition(x if cleaner is None else cleaner(x), [""] * x.shape[0])
+    if decode_fn is None:
+        if cldm.vae is None:
+            raise RuntimeError("restore_image: pass decode_fn, or build ControlLDM with vae_cfg")
+        decode_fn = lambda z: (cldm.vae_decode(z) + 1) / 2
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     pil_tiles = T.split_image_with_overlap(lq, T.LQ_PATCH, T.LQ_OVERLAP)
@@ -69,7 +81,8 @@ def restore_image(lq: np.ndarray, cldm, sampler, *, cond_fn: Callable, decode_fn
         try:
             if ts_model is not None:
                 z, _ = sampler.val_sample(cldm, dev, steps, (b, 4, 64, 64), cond, uncond, cfg_scale, x_T=x_T,
-                                          progress=False, cfg=cfg, pure_cldm=cldm, ts_model=ts_model)
+                                          progress=False, cfg=cfg, pure_cldm=cldm, ts_model=ts_model,
+                                          use_cuda_graph=use_cuda_graph)
             else:
                 z, _ = sampler.sample(cldm, dev, steps, (b, 4, 64, 64), cond, uncond, cfg_scale, x_T=x_T, progress=False,
                                       use_cuda_graph=use_cuda_graph)

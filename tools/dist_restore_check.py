@@ -1,6 +1,9 @@
 """Multi-GPU check of the tile-sharded restoration path (BASELINE config 4 geometry: 512x512 LQ -> 25 tiles -> 2048^2).
-Run with torchrun.  Uses clearly-labelled STAND-INS for the stages that are not on our kernels yet (cond / decode), so it
-validates sharding + NCCL all-gather + blend and W-independence of the result, and times the denoise+gather+blend part."""
+Run with torchrun.  FULL=1 (default): the whole path on our kernels — VAE encode + CLIP text encoder -> 50-step denoise
+(+ TESTR head and per-step prompt re-encoding when TESTR=1) -> VAE decode -> NCCL all-gather -> blend; the SwinIR
+cleaner is the identity and the tokenizer a hash (neither SwinIR nor the CLIP merge table ship here).  FULL=0: cheap
+stand-ins for cond / decode (sharding + all-gather + blend only).  Asserts that all ranks (and, with EXPECT_CRC, all
+world sizes) produce the same bits."""
 import os, sys, time, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,8 +23,32 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-model = ControlLDM(*full_cfgs()).to(dev).eval()
+FULL = os.environ.get("FULL", "1") == "1"
+TESTR = os.environ.get("TESTR", "0") == "1"
+unet_cfg, cn_cfg = full_cfgs()
+if FULL:
+    vae_cfg = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                 ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0), embed_dim=4)
+    clip_cfg = dict(embed_dim=1024, vision_cfg=None, layer="penultimate",
+                    text_cfg=dict(context_length=77, vocab_size=49408, width=1024, heads=16, layers=24))
+    model = ControlLDM(unet_cfg, vae_cfg, clip_cfg, cn_cfg).to(dev).eval()
+    def hash_tokenizer(texts):
+        out = torch.zeros((len(texts), 77), dtype=torch.long)
+        for i, s_ in enumerate(texts):
+            ids = [49406] + [zlib.crc32(w.encode()) % 49000 for w in s_.split()][:75] + [49407]
+            out[i, :len(ids)] = torch.tensor(ids)
+        return out
+    model.clip.attach_tokenizer(hash_tokenizer)
+else:
+    model = ControlLDM(unet_cfg, cn_cfg).to(dev).eval()
 nondegenerate_init_(model, 1234)
+det = None
+if TESTR:
+    from types import SimpleNamespace
+    from tair_b200.testr import TransformerDetector, default_cfg
+    det = TransformerDetector(default_cfg("cuda")).to(dev).eval(); nondegenerate_init_(det, 99)
+    model.return_nhwc_feats = True
+    vcfg = SimpleNamespace(exp_args=SimpleNamespace(mode="VAL", prompt_style="CAPTION"))
 sampler = SpacedSampler(val_diffusion().betas, "v", False)
 rng = np.random.default_rng(0)
 lq = rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)
@@ -39,7 +66,9 @@ def run(group_world):
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
-    out = pipeline.restore_image(lq, model, sampler, cond_fn=cond_fn, decode_fn=decode_fn, steps=steps, tile_batch=16)
+    kw = {} if FULL else dict(cond_fn=cond_fn, decode_fn=decode_fn)
+    if det is not None: kw.update(ts_model=det, cfg=vcfg)
+    out = pipeline.restore_image(lq, model, sampler, steps=steps, tile_batch=16, **kw)
     torch.cuda.synchronize()
     return out, time.perf_counter() - t0
 
@@ -51,7 +80,7 @@ if world > 1:
     dist.all_gather_object(crcs, crc)
     assert len(set(crcs)) == 1, f"ranks disagree on the stitched image: {crcs}"
 if rank == 0:
-    print(f"world={world} tiles=25 steps={steps} out={tuple(out.shape)} crc={crc:08x} time={dt:.3f}s patches/s={25 / dt:.2f}", flush=True)
+    print(f"full={int(FULL)} testr={int(TESTR)} world={world} tiles=25 steps={steps} out={tuple(out.shape)} crc={crc:08x} time={dt:.3f}s patches/s={25 / dt:.2f}", flush=True)
     exp = os.environ.get("EXPECT_CRC")
     if exp:
         assert f"{crc:08x}" == exp, f"result depends on world size: {crc:08x} vs {exp}"
