@@ -46,24 +46,34 @@ class TransformerDetector(nn.Module):
         """transformer_detector.py:123-152: softmax over the vocabulary, score = sigmoid(mean point logit),
         threshold, scale control points to pixels, arg-max characters."""
         assert len(ctrl_point_cls) == len(image_sizes)
+        # Batched: ONE device->host copy (the B x Q keep mask) instead of a boolean-mask sync per image and field; every
+        # field is gathered once for the whole batch and split into per-image views on the host-known counts.
+        B, Q = ctrl_point_cls.shape[:2]
+        dev = ctrl_point_cls.device
         text_pred = torch.softmax(text_pred, dim=-1)
         prob = ctrl_point_cls.mean(-2).sigmoid()
         scores, labels = prob.max(-1)
+        recs = text_pred.topk(1)[1].squeeze(-1)
+        scale = torch.tensor([[float(sz[1]), float(sz[0])] for sz in image_sizes], dtype=ctrl_point_coord.dtype).to(dev, non_blocking=True)
+        pts_px = ctrl_point_coord * scale[:, None, None, :]
+        keep = (scores >= self.test_score_threshold).cpu().numpy()
+        counts = keep.sum(1).tolist()
+        flat = torch.from_numpy(keep.reshape(-1).nonzero()[0]).to(dev, non_blocking=True)
+        g_scores = scores.reshape(B * Q).index_select(0, flat).split(counts)
+        g_labels = labels.reshape(B * Q).index_select(0, flat).split(counts)
+        g_pts = pts_px.reshape(B * Q, -1).index_select(0, flat).split(counts)
+        g_txt = text_pred.reshape(B * Q, *text_pred.shape[2:]).index_select(0, flat).split(counts)
+        g_recs = recs.reshape(B * Q, -1).index_select(0, flat).split(counts)
         results = []
-        for s, lab, pts, txt, size in zip(scores, labels, ctrl_point_coord, text_pred, image_sizes):
-            keep = s >= self.test_score_threshold
-            pts = pts[keep].clone()
-            pts[..., 0] *= size[1]
-            pts[..., 1] *= size[0]
-            txt = txt[keep]
+        for i, size in enumerate(image_sizes):
             r = Instances(size)
-            r.scores = s[keep]
-            r.pred_classes = lab[keep]
-            r.rec_scores = txt
+            r.scores = g_scores[i]
+            r.pred_classes = g_labels[i]
+            r.rec_scores = g_txt[i]
             if self.use_polygon:
-                r.polygons = pts.flatten(1)
+                r.polygons = g_pts[i]
             else:
-                r.beziers = pts.flatten(1)
-            r.recs = txt.topk(1)[1].squeeze(-1)
+                r.beziers = g_pts[i]
+            r.recs = g_recs[i]
             results.append(r)
         return results

@@ -26,6 +26,18 @@ def timeit(fn, n=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 
+from tair_b200.model.clip import FrozenOpenCLIPEmbedder
+clip = FrozenOpenCLIPEmbedder(1024, None, dict(context_length=77, vocab_size=49408, width=1024, heads=16, layers=24),
+                              layer="penultimate").to(dev).eval(); nondegenerate_init_(clip, 7)
+import zlib
+def hash_tok(texts):
+    out = torch.zeros((len(texts), 77), dtype=torch.long)
+    for i, s_ in enumerate(texts):
+        ids = [49406] + [zlib.crc32(w.encode()) % 49000 for w in s_.split()][:75] + [49407]
+        out[i, :len(ids)] = torch.tensor(ids)
+    return out
+clip.attach_tokenizer(hash_tok)
+
 res = {}
 for B in (1, 16):
     g = torch.Generator(device=dev).manual_seed(B)
@@ -48,6 +60,14 @@ for B in (1, 16):
     # inference post-processing (dynamic shapes + D2H): eager
     dense = det.testr(eager_unet()[1])
     r["inference_ms"] = timeit(lambda: [len(q) for q in det.inference(dense["pred_logits"], dense["pred_ctrl_points"], dense["pred_texts"], [(512, 512)] * B)])
+    # prompt re-encoding: B distinct new prompts through the 23 causal CLIP blocks (cache cleared = worst case)
+    cnt = [0]
+    def clip_new():
+        cnt[0] += 1
+        clip.clear_cache()
+        return clip.encode([f"A realistic scene where the texts word{cnt[0]} tile{i} appear clearly" for i in range(B)])
+    r["clip_encode_new_prompts_ms"] = timeit(clip_new)
+    r["full_step_ms_incl_inference_and_clip"] = r["graph_full_ms"] + r["inference_ms"] + r["clip_encode_new_prompts_ms"]
     res[f"B{B}"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()}
     print(B, res[f"B{B}"], flush=True)
 json.dump(res, open("gpurun_out/step_times.json", "w"), indent=1)
