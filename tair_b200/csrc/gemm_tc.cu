@@ -48,7 +48,7 @@ struct GemmParams {
   int conv;        // 0 plain, 1 conv3x3
   int kb_per_tap;  // Cin / 64
   int Ho, Wo, stride, pad;
-  int vec_out, vec_res, vec_rg;
+  int vec_out, vec_res, vec_rg, vec_bias;
   int tma_store;  // bf16 output eligible for the TMA-store epilogue
   int splits;      // split-K: each tile is computed by `splits` CTAs over kb_split k-blocks each; fp32 partials go to
   int kb_split;    // rows [split*M, split*M + M) of the (workspace) output, a second kernel reduces + applies the epilogue
@@ -297,13 +297,29 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
               r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + t.w);
             }
           }
+          // null checks hoisted out of the element loop: a predicated-off load still costs its address arithmetic
+          // and issue slots (ncu: ~33 issued instructions per output element before, most of them @!P LEA / LDG)
+          if (rg != nullptr && !p.vec_rg) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(r[j]);
-            if (e.bias != nullptr) a += __ldg(e.bias + n + j);
-            if (rg != nullptr && !p.vec_rg) a += __ldg(rg + n + j);
-            v[j] = apply_act<ACT>(a);
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(rg + n + j));
           }
+          if (e.bias != nullptr) {
+            if (p.vec_bias) {   // 16-byte loads, the same address in every lane (broadcast)
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n) + q);
+                r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + t.x);
+                r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + t.y);
+                r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + t.z);
+                r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + t.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(e.bias + n + j));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(__uint_as_float(r[j]));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -892,6 +908,7 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   }
   const int esz = e->out_fp32 ? 4 : 2;
   p.vec_out = ((reinterpret_cast<uintptr_t>(e->out) % 16) == 0) && ((e->ldc * esz) % 16 == 0);
+  p.vec_bias = e->bias && ((reinterpret_cast<uintptr_t>(e->bias) % 16) == 0);
   p.vec_rg = e->rowgroup && ((reinterpret_cast<uintptr_t>(e->rowgroup) % 16) == 0) && (e->ldg % 4 == 0);
   p.vec_res = e->residual && ((reinterpret_cast<uintptr_t>(e->residual) % 16) == 0) &&
               ((e->ldr * 2) % 16 == 0);
