@@ -240,8 +240,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       for (int q = 0; q < 4; ++q) rpre[q] = __ldg(reinterpret_cast<const uint4*>(resp + n + q * 8));
     }
   };
-  const bool has_res = e.residual != nullptr;   // warp-uniform: keeps the prefetch bookkeeping off the plain path
-  if (has_res && half < NSUB) prefetch(n_out0 + half * 64);
+  if (half < NSUB) prefetch(n_out0 + half * 64);
   mbar_wait(tfull_bar_addr, tfull_phase);
   tc_fence_after();
   if (half >= NSUB) {  // nothing to drain for this warp (narrow tiles): just release the accumulator
@@ -261,9 +260,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       float v[32];
       const int n = n_out0 + c0 + g;                   // first output column of this 32-wide group
       uint4 rcur[4];
-      if (has_res) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rcur[q] = rpre[q];
+      for (int q = 0; q < 4; ++q) rcur[q] = rpre[q];
+      {
         const int n_next = (g + 32 < ncol) ? n + 32 : n_out0 + (s + 2) * 64;   // next group of this warp, if any
         if ((g + 32 < ncol) || (s + 2 < NSUB)) prefetch(n_next);
       }
@@ -333,7 +332,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
           }
         }
       }
-      if (has_res && resp != nullptr) {
+      if (resp != nullptr) {
         if (res_vec_ok(n)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
