@@ -151,6 +151,16 @@ int tair_msda_forward(const void* value, const int64_t* spatial_shapes, const in
                       int32_t M, int32_t D, int32_t L, int32_t Lq, int32_t P, int32_t value_bf16,
                       int32_t out_bf16, void* stream);
 
+/* Tile front-end: crop P tiles of `tile` x `tile` pixels (origins[p] = {y, x}, device int32) out of the zero-padded
+ * 8-bit RGB image [Hp, Wp, 3] and resize each to out x out exactly as PIL's Image.resize(BICUBIC) does (two passes,
+ * 22-bit fixed point, 8-bit intermediate), then divide by 255: dst [P, 3, out, out] fp32.  bounds [out, 2] =
+ * {first tap, taps} and coeffs [out, ksize] int32 are PIL's per-output-index tables (same for both passes of a square
+ * tile; tair_b200.tiles.pil_bicubic_coeffs).  tmp: P * tile * out * 3 bytes.  Replaces the per-tile
+ * T.Resize(BICUBIC) + T.ToTensor() of val_patches.py:291-294,318. */
+int tair_tiles_bicubic_u8(const void* image, int32_t Hp, int32_t Wp, const int32_t* origins, int32_t P, int32_t tile,
+                          int32_t out, const int32_t* bounds, const int32_t* coeffs, int32_t ksize, void* tmp,
+                          float* dst, void* stream);
+
 /* Blend n_tiles fp32 tiles [n_tiles, C, tile, tile] laid out row-major on an n_h x n_w grid with the given
  * overlap (stride = tile - overlap) into out [C, out_h, out_w] (top-left crop of the canvas). */
 int tair_blend_tiles(const float* tiles, float* out, int32_t n_tiles, int32_t n_h, int32_t n_w, int32_t C,

@@ -65,6 +65,7 @@ SIGNATURES = {
     "tair_add_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "tair_upsample2x_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tair_msda_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tair_tiles_bicubic_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "tair_blend_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_msda_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_mha_small": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i64, _i32, _i64, _i64, _i64, _f32, _vp]),

@@ -471,6 +471,25 @@ def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_in
     return out
 
 
+def tiles_bicubic(image_u8: torch.Tensor, origins: torch.Tensor, bounds: torch.Tensor, coeffs: torch.Tensor,
+                  tile: int, out_size: int) -> torch.Tensor:
+    """image_u8 [Hp,Wp,3] uint8 (zero-padded LQ), origins [P,2] int32 (y,x) -> [P,3,out,out] fp32 in [0,1],
+    bit-identical to PIL BICUBIC + ToTensor per tile."""
+    _cuda(image_u8, "image", torch.uint8), _cuda(origins, "origins", torch.int32)
+    _cuda(bounds, "bounds", torch.int32), _cuda(coeffs, "coeffs", torch.int32)
+    if image_u8.dim() != 3 or image_u8.shape[2] != 3 or not image_u8.is_contiguous():
+        raise TairError("tiles_bicubic: image must be a contiguous [H,W,3] uint8 tensor")
+    P = origins.shape[0]
+    Hp, Wp = image_u8.shape[:2]
+    tmp = torch.empty((P, tile, out_size, 3), device=image_u8.device, dtype=torch.uint8)
+    dst = torch.empty((P, 3, out_size, out_size), device=image_u8.device, dtype=torch.float32)
+    rc = _lib.lib().tair_tiles_bicubic_u8(image_u8.data_ptr(), Hp, Wp, origins.contiguous().data_ptr(), P, tile, out_size,
+                                          bounds.contiguous().data_ptr(), coeffs.contiguous().data_ptr(), coeffs.shape[1],
+                                          tmp.data_ptr(), dst.data_ptr(), _stream())
+    _lib.check(rc, "tair_tiles_bicubic_u8")
+    return dst
+
+
 def softmax_rows(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x, "x", BF16)
     x2, ldx = _rows(x, "x")

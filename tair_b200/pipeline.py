@@ -65,14 +65,16 @@ def restore_image(lq: np.ndarray, cldm, sampler, *, cond_fn: Optional[Callable] 
         decode_fn = lambda z: (cldm.vae_decode(z) + 1) / 2
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    pil_tiles = T.split_image_with_overlap(lq, T.LQ_PATCH, T.LQ_OVERLAP)
-    n = len(pil_tiles)
+    # tile front-end on the GPU: the padded LQ image is uploaded once, tiles are cropped + resized on the device with
+    # PIL's exact fixed-point bicubic arithmetic (bit-identical to split_image_with_overlap + resize + ToTensor)
+    front = T.TileFrontEnd(lq, dev)
+    n = len(front)
     mine = T.shard_tiles(n, rank, world)
     decoded = []
     for s in range(0, len(mine), tile_batch):
         idx = mine[s:s + tile_batch]
         b = len(idx)
-        lq512 = torch.stack([_tile_to_tensor(pil_tiles[p]) for p in idx]).to(dev)
+        lq512 = front.tiles(idx)
         cond = cond_fn(lq512)
         uncond = uncond_fn(lq512) if (uncond_fn is not None and cfg_scale != 1.0) else None
         noise = _TileNoise(idx, seed, dev)

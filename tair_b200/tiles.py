@@ -46,6 +46,88 @@ def split_image_with_overlap(image, patch_size: int = LQ_PATCH, overlap: int = L
     return tiles
 
 
+# ---- PIL-exact bicubic resampling tables (host) and the GPU tile front-end ----------------------------------------
+
+def pil_bicubic_coeffs(in_size: int, out_size: int):
+    """Per-output-index windows and 22-bit fixed-point coefficients of PIL's Image.resize(BICUBIC) on 8-bit images
+    (Pillow src/libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc, bicubic a = -0.5, box = whole
+    tile).  Returns (bounds [out,2] int32 = first tap / number of taps, coeffs [out,ksize] int32)."""
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 2.0 * fscale
+    ksize = int(np.ceil(support)) * 2 + 1
+
+    def cubic(x):
+        a = -0.5
+        x = abs(x)
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0
+        if x < 2.0:
+            return (((x - 5.0) * x + 8.0) * x - 4.0) * a
+        return 0.0
+    bounds = np.zeros((out_size, 2), np.int32)
+    coeffs = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / fscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)           # C (int) cast: truncation; operands are positive here
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [cubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = sum(k)
+        if ww != 0.0:
+            k = [v / ww for v in k]
+        bounds[xx] = (xmin, xmax)
+        for x, v in enumerate(k):
+            coeffs[xx, x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+    return bounds, coeffs
+
+
+def resize_tile_reference(tile_u8: np.ndarray, out_size: int) -> np.ndarray:
+    """numpy restatement of the two fixed-point passes (used by the CPU test to pin the tables against PIL)."""
+    h, w = tile_u8.shape[:2]
+    bx, cx = pil_bicubic_coeffs(w, out_size)
+    by, cy = pil_bicubic_coeffs(h, out_size)
+    t = tile_u8.astype(np.int64)
+    tmp = np.zeros((h, out_size, 3), np.int64)
+    for ox in range(out_size):
+        x0, n = bx[ox]
+        tmp[:, ox] = np.clip(((1 << 21) + (t[:, x0:x0 + n] * cx[ox, :n, None].astype(np.int64)).sum(1)) >> 22, 0, 255)
+    out = np.zeros((out_size, out_size, 3), np.int64)
+    for oy in range(out_size):
+        y0, n = by[oy]
+        out[oy] = np.clip(((1 << 21) + (tmp[y0:y0 + n] * cy[oy, :n, None, None].astype(np.int64)).sum(0)) >> 22, 0, 255)
+    return out.astype(np.uint8)
+
+
+class TileFrontEnd:
+    """GPU replacement of split_image_with_overlap + per-tile PIL resize + ToTensor (val_patches.py:25-92,291-294,318):
+    the zero-padded LQ image is uploaded once; ``tiles(idx)`` crops and resizes any subset of tiles on the device."""
+
+    def __init__(self, image, device, patch_size: int = LQ_PATCH, overlap: int = LQ_OVERLAP, out_size: int = 512):
+        arr = np.asarray(image)
+        if arr.ndim == 2:
+            arr = np.repeat(arr[:, :, None], 3, axis=2)
+        h, w = arr.shape[:2]
+        self.rows, self.cols, ph, pw = tile_grid(h, w, patch_size, overlap)
+        canvas = np.zeros((ph, pw, 3), np.uint8)
+        canvas[:h, :w] = arr[:, :, :3]
+        self.image = torch.from_numpy(canvas).to(device)
+        stride = patch_size - overlap
+        self.origins = torch.tensor([[r * stride, c * stride] for r in range(self.rows) for c in range(self.cols)],
+                                    dtype=torch.int32, device=device)
+        b, c = pil_bicubic_coeffs(patch_size, out_size)
+        self.bounds, self.coeffs = torch.from_numpy(b).to(device), torch.from_numpy(c).to(device)
+        self.patch_size, self.out_size = patch_size, out_size
+
+    def __len__(self) -> int:
+        return self.rows * self.cols
+
+    def tiles(self, indices) -> torch.Tensor:
+        idx = torch.as_tensor(list(indices), dtype=torch.long, device=self.image.device)
+        return ops.tiles_bicubic(self.image, self.origins.index_select(0, idx), self.bounds, self.coeffs,
+                                 self.patch_size, self.out_size)
+
+
 def merge_patches_with_overlap(patches: Sequence[torch.Tensor], original_size: Tuple[int, int], patch_size: int = 512,
                                overlap: int = 64) -> torch.Tensor:
     """list of (1,3,P,P) CUDA tensors (row-major tile order) -> (1,3,scale*H,scale*W) blended image.

@@ -99,3 +99,18 @@ def test_restore_image_full_path_on_kernels(cuda_lib, manifests):
     assert torch.equal(a, b)
     with pytest.raises(RuntimeError):
         pipeline.restore_image(lq, narrow_model(manifests), sampler, steps=1)
+
+
+def test_gpu_tile_front_end_is_bit_identical_to_pil(cuda_lib):
+    """TileFrontEnd (crop + PIL-exact bicubic + /255 on the device) against the reference's host path:
+    split_image_with_overlap -> PIL resize(BICUBIC) -> ToTensor, for an image that needs right/bottom padding."""
+    from tair_b200 import pipeline, tiles as T
+    lq = np.random.default_rng(5).integers(0, 256, (200, 300, 3), dtype=np.uint8)
+    pil_tiles = T.split_image_with_overlap(lq, T.LQ_PATCH, T.LQ_OVERLAP)
+    ref = torch.stack([pipeline._tile_to_tensor(t) for t in pil_tiles])
+    front = T.TileFrontEnd(lq, torch.device("cuda"))
+    assert len(front) == len(pil_tiles) == 6
+    got = front.tiles(range(len(front)))
+    assert got.shape == (6, 3, 512, 512) and torch.equal(got.cpu(), ref)
+    sub = front.tiles([4, 1])
+    assert torch.equal(sub.cpu(), ref[[4, 1]])

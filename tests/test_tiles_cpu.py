@@ -71,3 +71,24 @@ def test_gather_tiles_world2_restores_global_order(n_tiles):
         assert p.exitcode == 0
     for _, order in got:
         assert order == [float(i) for i in range(n_tiles)]
+
+
+def test_bicubic_tables_reproduce_pil_exactly():
+    """The host tables behind the GPU tile front-end (tiles.pil_bicubic_coeffs) against PIL itself: the numpy
+    restatement of the two fixed-point passes must give PIL's Image.resize(BICUBIC) bytes."""
+    from PIL import Image
+    from tair_b200.tiles import pil_bicubic_coeffs, resize_tile_reference
+    rng = np.random.default_rng(3)
+    cases = [rng.integers(0, 256, (128, 128, 3), dtype=np.uint8) for _ in range(2)]
+    edge = np.zeros((128, 128, 3), np.uint8)
+    edge[37:90, 11:77] = 255
+    cases.append(edge)
+    for t in cases:
+        ref = np.asarray(Image.fromarray(t).resize((512, 512), Image.BICUBIC))
+        assert np.array_equal(resize_tile_reference(t, 512), ref)
+    small = rng.integers(0, 256, (16, 24, 3), dtype=np.uint8)          # non-square, other ratios
+    ref = np.asarray(Image.fromarray(small).resize((40, 40), Image.BICUBIC))
+    assert np.array_equal(resize_tile_reference(small, 40), ref)
+    b, c = pil_bicubic_coeffs(128, 512)
+    assert b.shape == (512, 2) and c.shape == (512, 5) and (b[:, 1] <= 5).all()
+    assert np.abs(c.sum(1) - (1 << 22)).max() <= 3                       # rows sum to 1.0 in 22-bit fixed point
