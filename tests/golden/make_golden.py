@@ -176,6 +176,32 @@ def gen_clip():
     print("clip_text: z std", z.std().item(), "keys", len(man))
 
 
+SWINIR_CFG = dict(img_size=64, patch_size=1, in_chans=3, embed_dim=180, depths=[6] * 8, num_heads=[6] * 8, window_size=8,
+                  mlp_ratio=2, sf=8, img_range=1.0, upsampler="nearest+conv", resi_connection="1conv", unshuffle=True,
+                  unshuffle_scale=8)
+
+
+def gen_swinir():
+    H.install()
+    from terediff.model.swinir import SwinIR
+    m = SwinIR(**SWINIR_CFG).eval()
+    man = Wt.manifest_of(m)
+    sd = Wt.seeded_state_dict(man)
+    # keep the integer index buffer and the 0/-100 masks of the reference, seed everything else
+    for k, v in m.state_dict().items():
+        if k.endswith("relative_position_index") or k.endswith("attn_mask"):
+            sd[k] = v.clone()
+    m.load_state_dict(sd)
+    x = torch.rand((1, 3, 128, 128), generator=torch.Generator().manual_seed(81))
+    with torch.no_grad():
+        y = m(x)
+    mf = json.load(open(os.path.join(HERE, "manifests.json")))
+    mf["swinir"] = man
+    json.dump(mf, open(os.path.join(HERE, "manifests.json"), "w"))
+    np.savez_compressed(os.path.join(HERE, "swinir.npz"), x=x.numpy(), y=y.numpy())
+    print("swinir: y std", y.std().item(), "keys", len(man))
+
+
 TOKENIZER_CASES = ["", "A realistic scene where the texts \"HELLO\", \"world\" appear clearly on signs.",
                    "it's  a  test &amp;amp; more!!!  123 4.5", "na\u00efve caf\u00e9 \u2014 \u65e5\u672c\u8a9e", "x" * 400,
                    "<start_of_text> hi <end_of_text>", "don't we'll I'm they've you'd HE'S", "  \t\n  ",
@@ -200,4 +226,4 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     for w in what:
         {"manifest": gen_manifest, "unet": gen_unet, "sched": gen_sched, "msda": gen_msda, "merge": gen_merge,
-         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip, "tok": gen_tok}[w]()
+         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip, "tok": gen_tok, "swinir": gen_swinir}[w]()

@@ -142,3 +142,17 @@ def test_clip_text_encoder_matches_reference_fixture(golden, manifests):
         z = OC.encode_tokens(sd, torch.from_numpy(g["tokens"]))
     assert z.shape == (2, 77, 1024)
     assert np.abs(z.numpy()[:, ::4, ::2] - g["z"]).max() < 2e-3
+
+
+def test_swinir_matches_reference_fixture(golden, manifests):
+    from oracle import swinir as OS
+    g = golden("swinir.npz")
+    sd = _swinir_state(manifests)
+    with torch.no_grad():
+        y = OS.swinir_forward(sd, torch.from_numpy(g["x"]))
+    assert y.shape == (1, 3, 128, 128)
+    assert np.abs(y.numpy() - g["y"]).max() < 2e-4
+
+
+def _swinir_state(manifests):
+    return weights.seeded_state_dict(manifests["swinir"])
