@@ -151,6 +151,27 @@ int tair_msda_forward(const void* value, const int64_t* spatial_shapes, const in
                       int32_t M, int32_t D, int32_t L, int32_t Lq, int32_t P, int32_t value_bf16,
                       int32_t out_bf16, void* stream);
 
+/* Window attention of the Swin blocks (terediff/model/swinir.py:120-149): n_windows back-to-back sequences of L <= 64
+ * tokens, H heads in 64-column slots (narrower heads zero-padded), packed 128/L per tensor-core tile and attended
+ * block-diagonally.  bias (or NULL): fp32 [bias_nw, H, L (key), L (query)], added to q.k BEFORE the scale, i.e. the
+ * caller stores (relative_position_bias + shift mask) / scale; window w uses table w % bias_nw. */
+int tair_attention_windows_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                                int32_t H, int32_t L, int64_t n_windows, const float* bias, int32_t bias_nw,
+                                float scale, void* stream);
+
+/* LayerNorm over the first C_valid channels of rows padded to C (C % 8 == 0, C <= 256); pad channels are written as 0.
+ * SwinIR keeps its 180 channels in 192-wide rows (swinir.py norm1 / norm2 / patch_embed.norm / norm). */
+int tair_layernorm_ragged(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                          int32_t M, int32_t C, int32_t C_valid, float eps, void* stream);
+
+/* y[r, :cols] = x[idx[r], :cols] (bf16 rows, cols % 8 == 0): window partition / reverse and cyclic shift of the Swin
+ * blocks as a single index map (swinir.py:37-66,262-281). */
+int tair_gather_rows_bf16(const void* x, int64_t ldx, const int32_t* idx, void* y, int64_t ldy, int64_t rows,
+                          int32_t cols, void* stream);
+
+/* y = x >= 0 ? x : slope * x on n bf16 values (n % 8 == 0): nn.LeakyReLU of the SwinIR upsampler (swinir.py:777-801). */
+int tair_leaky_relu_bf16(const void* x, void* y, int64_t n, float slope, void* stream);
+
 /* Tile front-end: crop P tiles of `tile` x `tile` pixels (origins[p] = {y, x}, device int32) out of the zero-padded
  * 8-bit RGB image [Hp, Wp, 3] and resize each to out x out exactly as PIL's Image.resize(BICUBIC) does (two passes,
  * 22-bit fixed point, 8-bit intermediate), then divide by 255: dst [P, 3, out, out] fp32.  bounds [out, 2] =

@@ -65,6 +65,10 @@ SIGNATURES = {
     "tair_add_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "tair_upsample2x_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tair_msda_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tair_attention_windows_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _vp, _i32, _f32, _vp]),
+    "tair_layernorm_ragged": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+    "tair_gather_rows_bf16": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "tair_leaky_relu_bf16": (C.c_int, [_vp, _vp, _i64, _f32, _vp]),
     "tair_tiles_bicubic_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "tair_blend_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_msda_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -47,6 +47,8 @@ struct AttnParams {
   int group;         // > 0: block-diagonal mode — the rows are back-to-back sequences of `group` tokens, a tile packs
                      // tile_rows / group of them and every row only sees the keys of its own sequence
   int tile_rows;     // query rows per CTA: 128, or (128 / group) * group in block-diagonal mode
+  const float* bias; // block-diagonal mode only: additive table [bias_nw][H][group (key)][group (query)] in units of
+  int bias_nw;       // 1/scale (S + table, then * scale); sequence w uses table w % bias_nw (Swin window masks)
   int q_tiles, nblk;
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* o;
@@ -215,6 +217,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);   // S(j) now lives in registers: the MMA warp may start S(j+1)
+      if (p.bias != nullptr) {     // relative-position bias (+ shifted-window mask): lanes = consecutive query rows
+        const int gsz = p.group;
+        const int wq = (q0 + r) / gsz;                       // global sequence (window) index of this row
+        const float* tb = p.bias + (((int64_t)(wq % p.bias_nw) * p.H + h) * gsz) * gsz + (r - klo);
+#pragma unroll
+        for (int i = 0; i < AT_BN; ++i)
+          if (i >= klo && i < kvalid) sv[i] = __float_as_uint(__uint_as_float(sv[i]) + __ldg(tb + (i - klo) * gsz));
+      }
       float mx;
       {
         float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
@@ -353,10 +363,11 @@ int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int6
 int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                      int64_t ldo, int H, int Lq, int Lk, int64_t n_outer, int n_inner, int64_t q_outer, int64_t q_inner,
                      int64_t q_tok, int64_t kv_outer, int64_t kv_inner, int64_t kv_tok, float scale, int causal,
-                     void* stream, int group = 0) {
+                     void* stream, int group = 0, const float* bias = nullptr, int bias_nw = 1) {
   AttnParams p{};
   p.causal = causal;
   p.group = group;
+  p.bias = bias; p.bias_nw = bias_nw;
   p.tile_rows = group > 0 ? (AT_BM / group) * group : AT_BM;
   p.H = H; p.Lq = Lq; p.Lk = Lk; p.n_inner = n_inner;
   p.q_tiles = (Lq + p.tile_rows - 1) / p.tile_rows;
@@ -419,4 +430,17 @@ extern "C" int tair_attention_seq_bf16(const void* q, const void* k, const void*
                             scale, 0, stream, L);
   return launch_attention(q, ld, k, ld, v, ld, o, ldo, H, L, L, n_outer, n_inner, outer_stride, inner_stride,
                           tok_stride, outer_stride, inner_stride, tok_stride, scale, 0, stream);
+}
+
+extern "C" int tair_attention_windows_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                                           int32_t H, int32_t L, int64_t n_windows, const float* bias, int32_t bias_nw,
+                                           float scale, void* stream) {
+  TAIR_REQUIRE(q && k && v && o, "attention_windows: NULL pointer");
+  TAIR_REQUIRE(H > 0 && L > 0 && L <= 64 && n_windows > 0 && n_windows * L < (1ll << 31), "attention_windows: bad shape");
+  TAIR_REQUIRE(bias == nullptr || bias_nw > 0, "attention_windows: bias_nw must be positive");
+  TAIR_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ld >= H * 64 && ldo >= H * 64, "attention_windows: bad row strides");
+  for (const void* ptr : {q, k, v, (const void*)o})
+    TAIR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) % 16) == 0, "attention_windows: pointers must be 16-byte aligned");
+  return launch_attention(q, ld, k, ld, v, ld, o, ldo, H, (int)(n_windows * L), (int)(n_windows * L), 1, 1, 0, 0, 1, 0, 0, 1,
+                          scale, 0, stream, L, bias, bias_nw);
 }

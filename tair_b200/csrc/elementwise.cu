@@ -343,3 +343,60 @@ extern "C" int tair_transpose_bf16(const void* in, int64_t ldi, int64_t in_batch
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("transpose_bf16_kernel");
 }
+
+// ---- row gather (window partition / cyclic shift of the SwinIR blocks as one index map, swinir.py:37-66,262-281) and
+// LeakyReLU (swinir.py:777-801) ----
+namespace tair {
+namespace {
+__global__ void gather_rows_kernel(const uint4* __restrict__ x, int64_t ldx16, const int32_t* __restrict__ idx,
+                                   uint4* __restrict__ y, int64_t ldy16, int64_t rows, int vec_per_row) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * vec_per_row) return;
+  const int64_t r = t / vec_per_row;
+  const int v = (int)(t - r * vec_per_row);
+  y[r * ldy16 + v] = __ldg(x + (int64_t)__ldg(idx + r) * ldx16 + v);
+}
+
+__global__ void leaky_relu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t n16, float slope) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n16) return;
+  const uint4 q = __ldg(x + t);
+  const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+  uint32_t out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = unpack_bf16(in[i]);
+    f.x = f.x >= 0.f ? f.x : f.x * slope;
+    f.y = f.y >= 0.f ? f.y : f.y * slope;
+    out[i] = pack_bf16(f.x, f.y);
+  }
+  y[t] = make_uint4(out[0], out[1], out[2], out[3]);
+}
+}  // namespace
+}  // namespace tair
+
+extern "C" int tair_gather_rows_bf16(const void* x, int64_t ldx, const int32_t* idx, void* y, int64_t ldy, int64_t rows,
+                                     int32_t cols, void* stream) {
+  TAIR_REQUIRE(x && idx && y, "gather_rows: NULL pointer");
+  TAIR_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cols && ldy >= cols,
+               "gather_rows: cols and row strides must be multiples of 8");
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(y) % 16) == 0,
+               "gather_rows: tensors must be 16-byte aligned");
+  const int vpr = cols / 8;
+  const int64_t total = rows * vpr;
+  tair::gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), ldx / 8, idx, reinterpret_cast<uint4*>(y), ldy / 8, rows, vpr);
+  tair::g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return tair::check_launch("gather_rows_kernel");
+}
+
+extern "C" int tair_leaky_relu_bf16(const void* x, void* y, int64_t n, float slope, void* stream) {
+  TAIR_REQUIRE(x && y && n > 0 && n % 8 == 0, "leaky_relu: n must be a positive multiple of 8");
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(y) % 16) == 0,
+               "leaky_relu: tensors must be 16-byte aligned");
+  const int64_t n16 = n / 8;
+  tair::leaky_relu_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n16, slope);
+  tair::g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return tair::check_launch("leaky_relu_kernel");
+}

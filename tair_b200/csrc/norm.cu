@@ -223,6 +223,54 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld
   }
 }
 
+
+// LayerNorm over the first Cv channels of rows that are padded to C (C % 8 == 0, C <= 256): the SwinIR trunk keeps its
+// 180 channels in 192-wide rows so that every GEMM / conv operand is TMA-legal; pad channels are written as zeros.
+__global__ void layernorm_ragged_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                        int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        int M, int C, int Cv, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  float v[8];
+  float s = 0.f;
+  const bool have = lane < nvec;
+  if (have) {
+    load8(x + (int64_t)row * ldx + lane * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane * 8 + i >= Cv) v[i] = 0.f;
+      s += v[i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)Cv;
+  float q = 0.f;
+  if (have) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane * 8 + i < Cv) {
+        const float d = v[i] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)Cv + eps);
+  if (have) {
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane * 8 + i;
+      o8[i] = c < Cv ? (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.f;
+    }
+    store8(y + (int64_t)row * ldy + lane * 8, o8);
+  }
+}
+
 }  // namespace
 }  // namespace tair
 
@@ -296,4 +344,19 @@ extern "C" int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, 
   else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("layernorm_kernel");
+}
+
+extern "C" int tair_layernorm_ragged(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                                     const float* beta, int32_t M, int32_t C, int32_t C_valid, float eps, void* stream) {
+  TAIR_REQUIRE(x && y && gamma && beta, "layernorm_ragged: NULL pointer");
+  TAIR_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && C <= 256 && C_valid > 0 && C_valid <= C,
+               "layernorm_ragged: needs C %% 8 == 0, C <= 256, 0 < C_valid <= C (C=%d, C_valid=%d)", C, C_valid);
+  TAIR_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C, "layernorm_ragged: bad row strides");
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(y) % 16) == 0,
+               "layernorm_ragged: tensors must be 16-byte aligned");
+  const int warps = 8;
+  layernorm_ragged_kernel<<<(M + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, gamma, beta, M, C, C_valid, eps);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("layernorm_ragged_kernel");
 }

@@ -1,0 +1,254 @@
+"""SwinIR cleaner on the sm_100a kernels (val_patches.py:324 runs it once per tile before
+``prepare_condition``).  Mirrors terediff/model/swinir.py:624-892 for the TeReDiff configuration (unshuffle 8,
+'nearest+conv' upsampler, '1conv' residual connection): same constructor keywords and the same ``state_dict`` names,
+so ``realesrgan_s4_swinir_100k.pth`` loads unchanged.
+
+Layout: the 180-channel trunk lives in 192-wide channels-last bf16 rows (TMA / UMMA k-blocks are 64 channels; the 12
+pad channels are kept at zero by zero-padded weights and a LayerNorm that normalises over the 180 real channels);
+the six 30-wide heads sit in 64-column slots of the fused q|k|v projection.  Per Swin block (swinir.py:245-288):
+ONE row gather replaces roll + window_partition (the inverse map of the previous block is folded into it), then
+LayerNorm -> qkv GEMM -> window attention on the tcgen05 kernel (two 8x8 windows per 128-row tile, block-diagonal,
+relative-position bias + shifted-window mask from a table) -> proj GEMM (+residual) -> LayerNorm -> fc1 (+GELU) ->
+fc2 (+residual), all in window order.  3x3 convs run on the implicit-GEMM kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+
+BF16 = torch.bfloat16
+CP = 192   # padded trunk width
+HS = 64    # head slot width
+RGB_MEAN = (0.4488, 0.4371, 0.4040)
+
+
+class _WindowAttention(nn.Module):
+    def __init__(self, dim: int, ws: int, heads: int):
+        super().__init__()
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) * (2 * ws - 1), heads))
+        coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")).flatten(1)
+        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += ws - 1
+        rel[:, :, 1] += ws - 1
+        rel[:, :, 0] *= 2 * ws - 1
+        self.register_buffer("relative_position_index", rel.sum(-1))
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+def _shift_mask(H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """swinir.py:222-243 -> (nW, N, N) of 0 / -100."""
+    img = torch.zeros((1, H, W, 1))
+    cnt = 0
+    for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, hs, wsl, :] = cnt
+            cnt += 1
+    m = img.view(1, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+    d = m.unsqueeze(1) - m.unsqueeze(2)
+    return torch.where(d != 0, torch.full_like(d, -100.0), torch.zeros_like(d))
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, res, heads, ws, shift, mlp_ratio):
+        super().__init__()
+        self.shift_size = shift
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _WindowAttention(dim, ws, heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+        self.register_buffer("attn_mask", _shift_mask(res[0], res[1], ws, shift) if shift > 0 else None)
+
+
+class _BasicLayer(nn.Module):
+    def __init__(self, dim, res, depth, heads, ws, mlp_ratio):
+        super().__init__()
+        self.blocks = nn.ModuleList([_Block(dim, res, heads, ws, 0 if i % 2 == 0 else ws // 2, mlp_ratio)
+                                     for i in range(depth)])
+
+
+class _RSTB(nn.Module):
+    def __init__(self, dim, res, depth, heads, ws, mlp_ratio):
+        super().__init__()
+        self.residual_group = _BasicLayer(dim, res, depth, heads, ws, mlp_ratio)
+        self.conv = nn.Conv2d(dim, dim, 3, 1, 1)
+
+
+class _Norm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+
+
+def _pad_rows(w: torch.Tensor, rows: int) -> torch.Tensor:
+    out = torch.zeros((rows,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
+    out[:w.shape[0]] = w
+    return out
+
+
+def _pack_conv(conv: nn.Conv2d, cin_pad: int, cout_pad: int):
+    w = conv.weight.detach()
+    co, ci = w.shape[:2]
+    wp = torch.zeros((cout_pad, 3, 3, cin_pad), device=w.device, dtype=BF16)
+    wp[:co, :, :, :ci] = w.permute(0, 2, 3, 1).to(BF16)
+    return wp.reshape(cout_pad, 9 * cin_pad).contiguous(), _pad_rows(conv.bias.detach().float(), cout_pad).contiguous()
+
+
+class SwinIR(nn.Module):
+    def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=180, depths=(6,) * 8, num_heads=(6,) * 8,
+                 window_size=8, mlp_ratio=2.0, sf=8, img_range=1.0, upsampler="nearest+conv", resi_connection="1conv",
+                 unshuffle=True, unshuffle_scale=8, **_ignored):
+        super().__init__()
+        if not (upsampler == "nearest+conv" and resi_connection == "1conv" and unshuffle and sf == 8 and
+                unshuffle_scale == 8 and patch_size == 1 and in_chans == 3 and img_range == 1.0):
+            raise NotImplementedError("tair_b200 SwinIR covers the TeReDiff configuration (unshuffle 8, nearest+conv x8, 1conv)")
+        if embed_dim > CP or embed_dim % num_heads[0] or embed_dim // num_heads[0] > HS or window_size != 8 or \
+                len(set(num_heads)) != 1 or int(embed_dim * mlp_ratio) % 8:
+            raise NotImplementedError("tair_b200 SwinIR: embed_dim <= 192, head width <= 64, window 8")
+        self.embed_dim, self.heads, self.ws, self.upscale = embed_dim, num_heads[0], window_size, sf
+        res = (img_size, img_size)
+        self.conv_first = nn.Sequential(nn.PixelUnshuffle(sf), nn.Conv2d(in_chans * sf * sf, embed_dim, 3, 1, 1))
+        self.patch_embed = _Norm(embed_dim)
+        self.layers = nn.ModuleList([_RSTB(embed_dim, res, d, h, window_size, mlp_ratio) for d, h in zip(depths, num_heads)])
+        self.norm = nn.LayerNorm(embed_dim)
+        self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, 64, 3, 1, 1), nn.LeakyReLU(inplace=True))
+        self.conv_up1 = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_up2 = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_up3 = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_hr = nn.Conv2d(64, 64, 3, 1, 1)
+        self.conv_last = nn.Conv2d(64, in_chans, 3, 1, 1)
+        self._pk = None
+        self._geo: Dict[Tuple[int, int, int, torch.device], dict] = {}
+
+    # ---------------------------------------------------------------- packing
+    def _stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    @torch.no_grad()
+    def _packs(self) -> dict:
+        st = self._stamp()
+        if self._pk is not None and self._pk["stamp"] == st:
+            return self._pk
+        C, H, hd = self.embed_dim, self.heads, self.embed_dim // self.heads
+        scale = hd ** -0.5
+        N = self.ws * self.ws
+
+        def ln(m):
+            return _pad_rows(m.weight.detach().float(), CP).contiguous(), _pad_rows(m.bias.detach().float(), CP).contiguous()
+
+        pk = dict(stamp=st, first=_pack_conv(self.conv_first[1], CP, CP), pe=ln(self.patch_embed.norm), norm=ln(self.norm),
+                  after=_pack_conv(self.conv_after_body, CP, CP), before=_pack_conv(self.conv_before_upsample[0], CP, 64),
+                  up=[_pack_conv(c, 64, 64) for c in (self.conv_up1, self.conv_up2, self.conv_up3)],
+                  hr=_pack_conv(self.conv_hr, 64, 64), last=_pack_conv(self.conv_last, 64, 8), rstb=[])
+        for layer in self.layers:
+            blocks = []
+            for b in layer.residual_group.blocks:
+                a = b.attn
+                dev = a.qkv.weight.device
+                wq = torch.zeros((3, H, HS, CP), device=dev)
+                wq[:, :, :hd, :C] = a.qkv.weight.detach().view(3, H, hd, C)
+                bq = torch.zeros((3, H, HS), device=dev)
+                bq[:, :, :hd] = a.qkv.bias.detach().view(3, H, hd)
+                wp = torch.zeros((CP, H, HS), device=dev)
+                wp[:C, :, :hd] = a.proj.weight.detach().view(C, H, hd)
+                f1 = torch.zeros((b.mlp.fc1.weight.shape[0], CP), device=dev)
+                f1[:, :C] = b.mlp.fc1.weight.detach()
+                idx = a.relative_position_index.view(-1).long()
+                rb = a.relative_position_bias_table.detach()[idx].view(N, N, H).permute(2, 1, 0)   # [H, key, query]
+                blocks.append(dict(
+                    n1=ln(b.norm1), n2=ln(b.norm2),
+                    qkv=(wq.view(3 * H * HS, CP).to(BF16).contiguous(), bq.view(-1).float().contiguous()),
+                    proj=(wp.view(CP, H * HS).to(BF16).contiguous(), _pad_rows(a.proj.bias.detach().float(), CP).contiguous()),
+                    fc1=(f1.to(BF16).contiguous(), b.mlp.fc1.bias.detach().float().contiguous()),
+                    fc2=(_pad_rows(b.mlp.fc2.weight.detach(), CP).to(BF16).contiguous(),
+                         _pad_rows(b.mlp.fc2.bias.detach().float(), CP).contiguous()),
+                    bias=(rb.float() / scale).contiguous(), shift=b.shift_size))
+            pk["rstb"].append(dict(blocks=blocks, conv=_pack_conv(layer.conv, CP, CP)))
+        self._pk = pk
+        return pk
+
+    def _geometry(self, B: int, h: int, w: int, dev) -> dict:
+        """Row index maps token order <-> window order (plain and shifted), composed between consecutive blocks, and the
+        shifted-window mask for this grid."""
+        key = (B, h, w, dev)
+        g = self._geo.get(key)
+        if g is not None:
+            return g
+        ws, s = self.ws, self.ws // 2
+        tok = torch.arange(B * h * w).view(B, h, w)
+
+        def part(t):
+            return t.view(B, h // ws, ws, w // ws, ws).permute(0, 1, 3, 2, 4).reshape(-1)
+        p0 = part(tok)
+        ps = part(torch.roll(tok, shifts=(-s, -s), dims=(1, 2)))
+        inv0, invs = torch.empty_like(p0), torch.empty_like(ps)
+        inv0[p0] = torch.arange(p0.numel())
+        invs[ps] = torch.arange(ps.numel())
+        i32 = lambda t: t.to(torch.int32).to(dev)
+        g = dict(p0=i32(p0), ps=i32(ps), inv0=i32(inv0), invs=i32(invs), c0s=i32(inv0[ps]), cs0=i32(invs[p0]),
+                 mask=_shift_mask(h, w, ws, s).to(dev))
+        if len(self._geo) > 8:
+            self._geo.clear()
+        self._geo[key] = g
+        return g
+
+    # ---------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,3,H,W) fp32 in [0,1], H and W multiples of 64 -> cleaned image (B,3,H,W) fp32 (swinir.py:856-892)."""
+        B, _, Hh, Ww = x.shape
+        if Hh % 64 or Ww % 64:
+            raise ValueError("tair_b200 SwinIR needs image sides that are multiples of 64 (unshuffle 8 x window 8)")
+        pk = self._packs()
+        C, H, hd, N = self.embed_dim, self.heads, self.embed_dim // self.heads, self.ws * self.ws
+        scale = hd ** -0.5
+        mean = torch.tensor(RGB_MEAN, device=x.device, dtype=torch.float32).view(1, 3, 1, 1)
+        u = F.pixel_unshuffle(x.float() - mean, self.upscale)
+        h, w = u.shape[2:]
+        geo = self._geometry(B, h, w, x.device)
+        nwin = B * h * w // N
+        f0 = ops.conv3x3(ops.nchw_to_nhwc(u.contiguous(), CP), pk["first"][0], bias=pk["first"][1])   # [B,h,w,192]
+        t = ops.layernorm_ragged(f0.view(-1, CP), *pk["pe"], C)
+        bias_cache = {}
+        for rs in pk["rstb"]:
+            r, prev = t, None            # prev: shift of the block whose window order `r` is currently in
+            for blk in rs["blocks"]:
+                s = blk["shift"]
+                if prev is None:
+                    idx = geo["ps"] if s else geo["p0"]
+                else:
+                    idx = geo["c0s"] if s else geo["cs0"]
+                xw = ops.gather_rows(r, idx)
+                if s:
+                    tb = (blk["bias"].unsqueeze(0) + geo["mask"].transpose(1, 2).unsqueeze(1) / scale).contiguous()
+                else:
+                    tb = blk["bias"].unsqueeze(0).contiguous()
+                qkv = ops.gemm(ops.layernorm_ragged(xw, *blk["n1"], C), blk["qkv"][0], bias=blk["qkv"][1])
+                a = ops.attention_windows(qkv, n_heads=H, L=N, n_windows=nwin, scale=scale, bias=tb)
+                xw = ops.gemm(a, blk["proj"][0], bias=blk["proj"][1], residual=xw)
+                hmid = ops.gemm(ops.layernorm_ragged(xw, *blk["n2"], C), blk["fc1"][0], bias=blk["fc1"][1], act=ops.ACT_GELU)
+                r = ops.gemm(hmid, blk["fc2"][0], bias=blk["fc2"][1], residual=xw)
+                prev = s
+            r = ops.gather_rows(r, geo["invs"] if prev else geo["inv0"])
+            t = ops.conv3x3(r.view(B, h, w, CP), rs["conv"][0], bias=rs["conv"][1], residual=t.view(B, h, w, CP)).view(-1, CP)
+        t = ops.layernorm_ragged(t, *pk["norm"], C)
+        y = ops.conv3x3(t.view(B, h, w, CP), pk["after"][0], bias=pk["after"][1], residual=f0)
+        y = ops.leaky_relu(ops.conv3x3(y, pk["before"][0], bias=pk["before"][1]), 0.01)   # nn.LeakyReLU() default slope
+        for wu, bu in pk["up"]:
+            y = ops.leaky_relu(ops.conv3x3(ops.upsample2x(y), wu, bias=bu), 0.2)
+        y = ops.conv3x3(ops.leaky_relu(ops.conv3x3(y, pk["hr"][0], bias=pk["hr"][1]), 0.2), pk["last"][0], bias=pk["last"][1])
+        return ops.nhwc_to_nchw(y, 3) + mean

@@ -490,6 +490,63 @@ def tiles_bicubic(image_u8: torch.Tensor, origins: torch.Tensor, bounds: torch.T
     return dst
 
 
+def attention_windows(qkv: torch.Tensor, *, n_heads: int, L: int, n_windows: int, scale: float,
+                      bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Swin window attention: qkv bf16 [n_windows*L, 3*H*64] (q | k | v, 64-column head slots); bias fp32
+    [nw, H, L(key), L(query)] = (relative-position bias + mask) / scale, window w uses table w % nw."""
+    _cuda(qkv, "qkv", BF16)
+    q2, ld = _rows(qkv, "qkv")
+    E = n_heads * 64
+    if q2.shape[1] != 3 * E or q2.shape[0] != n_windows * L:
+        raise TairError(f"attention_windows: expected [{n_windows * L}, {3 * E}], got {tuple(q2.shape)}")
+    nw = 1
+    if bias is not None:
+        _cuda(bias, "bias", torch.float32)
+        if bias.dim() != 4 or tuple(bias.shape[1:]) != (n_heads, L, L) or not bias.is_contiguous():
+            raise TairError("attention_windows: bias must be contiguous [nw, H, L, L] fp32")
+        nw = bias.shape[0]
+    if out is None:
+        out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
+    o2, ldo = _rows(out, "out")
+    base = q2.data_ptr()
+    with _timed("attention_windows", 4.0 * n_windows * n_heads * L * L * 64, (n_windows, n_heads, L)):
+        rc = _lib.lib().tair_attention_windows_bf16(base, base + 2 * E, base + 4 * E, ld, o2.data_ptr(), ldo, n_heads, L,
+                                                    n_windows, None if bias is None else bias.data_ptr(), nw, float(scale),
+                                                    _stream())
+    _lib.check(rc, "tair_attention_windows_bf16")
+    return out
+
+
+def layernorm_ragged(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, c_valid: int, *, eps: float = 1e-5) -> torch.Tensor:
+    _cuda(x, "x", BF16), _cuda(gamma, "gamma", torch.float32), _cuda(beta, "beta", torch.float32)
+    x2, ldx = _rows(x, "x")
+    out = torch.empty_like(x2)
+    rc = _lib.lib().tair_layernorm_ragged(x2.data_ptr(), ldx, out.data_ptr(), out.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                          x2.shape[0], x2.shape[1], int(c_valid), float(eps), _stream())
+    _lib.check(rc, "tair_layernorm_ragged")
+    return out
+
+
+def gather_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _cuda(x, "x", BF16), _cuda(idx, "idx", torch.int32)
+    x2, ldx = _rows(x, "x")
+    out = torch.empty((idx.numel(), x2.shape[1]), device=x.device, dtype=BF16)
+    rc = _lib.lib().tair_gather_rows_bf16(x2.data_ptr(), ldx, idx.data_ptr(), out.data_ptr(), out.stride(0), idx.numel(),
+                                          x2.shape[1], _stream())
+    _lib.check(rc, "tair_gather_rows_bf16")
+    return out
+
+
+def leaky_relu(x: torch.Tensor, slope: float) -> torch.Tensor:
+    _cuda(x, "x", BF16)
+    if not x.is_contiguous():
+        raise TairError("leaky_relu: x must be contiguous")
+    out = torch.empty_like(x)
+    rc = _lib.lib().tair_leaky_relu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), float(slope), _stream())
+    _lib.check(rc, "tair_leaky_relu_bf16")
+    return out
+
+
 def softmax_rows(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x, "x", BF16)
     x2, ldx = _rows(x, "x")
