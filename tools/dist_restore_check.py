@@ -1,7 +1,8 @@
 """Multi-GPU check of the tile-sharded restoration path (BASELINE config 4 geometry: 512x512 LQ -> 25 tiles -> 2048^2).
 Run with torchrun.  FULL=1 (default): the whole path on our kernels — VAE encode + CLIP text encoder -> 50-step denoise
-(+ TESTR head and per-step prompt re-encoding when TESTR=1) -> VAE decode -> NCCL all-gather -> blend; the SwinIR
-cleaner is the identity and the tokenizer a hash (neither SwinIR nor the CLIP merge table ship here).  FULL=0: cheap
+(+ TESTR head and per-step prompt re-encoding when TESTR=1) -> VAE decode -> NCCL all-gather -> blend, with the SwinIR
+cleaner on the kernels in front (GPU tile front-end -> SwinIR -> VAE encode); the tokenizer is a hash (the CLIP
+merge table does not ship here).  FULL=0: cheap
 stand-ins for cond / decode (sharding + all-gather + blend only).  Asserts that all ranks (and, with EXPECT_CRC, all
 world sizes) produce the same bits."""
 import os, sys, time, zlib
@@ -39,6 +40,11 @@ if FULL:
             out[i, :len(ids)] = torch.tensor(ids)
         return out
     model.clip.attach_tokenizer(hash_tokenizer)
+    from tair_b200.model.swinir import SwinIR
+    cleaner = SwinIR(img_size=64, patch_size=1, in_chans=3, embed_dim=180, depths=[6] * 8, num_heads=[6] * 8, window_size=8,
+                     mlp_ratio=2, sf=8, img_range=1.0, upsampler="nearest+conv", resi_connection="1conv", unshuffle=True,
+                     unshuffle_scale=8).to(dev).eval()
+    nondegenerate_init_(cleaner, 77)
 else:
     model = ControlLDM(unet_cfg, cn_cfg).to(dev).eval()
 nondegenerate_init_(model, 1234)
@@ -66,7 +72,7 @@ def run(group_world):
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
-    kw = {} if FULL else dict(cond_fn=cond_fn, decode_fn=decode_fn)
+    kw = dict(cleaner=lambda x: cleaner(x).clamp(0, 1)) if FULL else dict(cond_fn=cond_fn, decode_fn=decode_fn)
     if det is not None: kw.update(ts_model=det, cfg=vcfg)
     out = pipeline.restore_image(lq, model, sampler, steps=steps, tile_batch=16, **kw)
     torch.cuda.synchronize()
