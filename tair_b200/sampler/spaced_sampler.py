@@ -154,8 +154,26 @@ class SpacedSampler(Sampler):
         want = [] if cfg is None else list(cfg.exp_args["unet_feat_sampling_timestep"])
         kept = []
         stepper = None
+        # The decoder features of a step are only returned for the steps listed in cfg (none by default): let the model
+        # hand them over channels-last bf16 and convert the few that are kept, instead of four NHWC->NCHW fp32
+        # transposes on every step (1 % of the step).
+        lazy = getattr(model, "return_nhwc_feats", None) is False
+        if lazy:
+            model.return_nhwc_feats = True
+        to_nchw = (lambda fs: [ops.nhwc_to_nchw(f) for f in fs]) if lazy else (lambda fs: fs)
+        try:
+            return self._sample_loop(model, device, x, order, total, bs, cond, uncond, cfg_scale, want, kept, to_nchw,
+                                     use_cuda_graph, lazy)
+        finally:
+            if lazy:
+                model.return_nhwc_feats = False
+
+    def _sample_loop(self, model, device, x, order, total, bs, cond, uncond, cfg_scale, want, kept, to_nchw,
+                     use_cuda_graph, lazy):
+        stepper = None
         if use_cuda_graph:
-            key = (id(model), tuple(x.shape), uncond is None, tuple(sorted((k, tuple(v.shape)) for k, v in cond.items())))
+            key = (id(model), tuple(x.shape), uncond is None, lazy,
+                   tuple(sorted((k, tuple(v.shape)) for k, v in cond.items())))
             stepper = self._graphs.get(key)
             if stepper is None:
                 stepper = self._graphs[key] = _StepGraph(self, model, x, cond, uncond)
@@ -170,7 +188,7 @@ class SpacedSampler(Sampler):
                 t = torch.full((bs,), total - i - 1, device=device, dtype=torch.long)
                 x, feats = self.p_sample(model, x, model_t, t, cond, uncond, scale, noise=self._noise(i, x))
             if i + 1 in want:
-                kept.append((i + 1, cur, [f.clone() for f in feats] if stepper is not None else feats))
+                kept.append((i + 1, cur, to_nchw([f.clone() for f in feats] if stepper is not None else feats)))
         return x, kept
 
     @torch.no_grad()
