@@ -12,6 +12,7 @@ from tair_b200.sampler import SpacedSampler
 B = int(os.environ.get("B", "16"))
 dev = torch.device("cuda:0")
 model = ControlLDM(*full_cfgs()).to(dev).eval(); nondegenerate_init_(model, 1234)
+model.overlap_controlnet = False   # one stream: per-launch event times must be per-kernel times
 s = SpacedSampler(val_diffusion().betas, "v", False); s.make_schedule(50); s.to(dev)
 g = torch.Generator(device=dev).manual_seed(B)
 x = torch.randn((B, 4, 64, 64), device=dev, generator=g)
