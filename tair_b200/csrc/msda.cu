@@ -229,9 +229,11 @@ template <> struct ProjVec<__nv_bfloat16> {
   }
 };
 
-template <typename PJ>
-__global__ void __launch_bounds__(256, 4) msda_fused44_kernel(const MsdaFusedParams p) {
-  constexpr int LP = 16, PER = ProjVec<PJ>::PER;
+// CPL = channels per lane (8 or 16): with 16 the per-(query, head) work that does not depend on the channel — softmax,
+// sampling coordinates, bilinear weights, addresses — is amortised over twice as many channels (2 lanes per item for D=32).
+template <typename PJ, int CPL>
+__global__ void __launch_bounds__(256, CPL == 8 ? 4 : 3) msda_fused44_kernel(const MsdaFusedParams p) {
+  constexpr int LP = 16, PER = ProjVec<PJ>::PER, NV = CPL / 8;
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long item = gtid / p.lanes_per_item;
   const int part = (int)(gtid - item * p.lanes_per_item);
@@ -258,11 +260,11 @@ __global__ void __launch_bounds__(256, 4) msda_fused44_kernel(const MsdaFusedPar
   for (int i = 0; i < LP; ++i) { w[i] = __expf(w[i] - mx); sum += w[i]; }
   const float inv = 1.f / sum;
   const float* refq = p.ref + (long)b * p.ref_batch_stride + (long)(q / p.q_per_ref) * 4 * p.ref_dim;
-  const __nv_bfloat16* vbase = p.value + ((long)b * p.S * p.M + m) * p.D + part * 8;
+  const __nv_bfloat16* vbase = p.value + ((long)b * p.S * p.M + m) * p.D + part * CPL;
   const int row_stride = p.M * p.D;
-  float acc[8];
+  float acc[CPL];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const int H = (int)__ldg(p.shapes + 2 * l), W = (int)__ldg(p.shapes + 2 * l + 1);
@@ -300,25 +302,32 @@ __global__ void __launch_bounds__(256, 4) msda_fused44_kernel(const MsdaFusedPar
       const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_low + 1, 0), H - 1);
       const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_low + 1, 0), W - 1);
       const uint32_t r0 = (uint32_t)y0 * wrs, r1 = (uint32_t)y1 * wrs, c0 = (uint32_t)x0 * rsb, c1 = (uint32_t)x1 * rsb;
-      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c0)));
-      const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c1)));
-      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(vlb + (r1 + c0)));
-      const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(vlb + (r1 + c1)));
       const float w1 = wt * wl, w2 = wt * wr, w3 = wb * wl, w4 = wb * wr;
-      const uint32_t a1[4] = {q1.x, q1.y, q1.z, q1.w}, a2[4] = {q2.x, q2.y, q2.z, q2.w};
-      const uint32_t a3[4] = {q3.x, q3.y, q3.z, q3.w}, a4[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 v1 = unpack_bf16(a1[i]), v2 = unpack_bf16(a2[i]), v3 = unpack_bf16(a3[i]), v4 = unpack_bf16(a4[i]);
-        acc[2 * i] = fmaf(w4, v4.x, fmaf(w3, v3.x, fmaf(w2, v2.x, fmaf(w1, v1.x, acc[2 * i]))));
-        acc[2 * i + 1] = fmaf(w4, v4.y, fmaf(w3, v3.y, fmaf(w2, v2.y, fmaf(w1, v1.y, acc[2 * i + 1]))));
+      for (int nv = 0; nv < NV; ++nv) {
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c0)) + nv);
+        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c1)) + nv);
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(vlb + (r1 + c0)) + nv);
+        const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(vlb + (r1 + c1)) + nv);
+        const uint32_t a1[4] = {q1.x, q1.y, q1.z, q1.w}, a2[4] = {q2.x, q2.y, q2.z, q2.w};
+        const uint32_t a3[4] = {q3.x, q3.y, q3.z, q3.w}, a4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 v1 = unpack_bf16(a1[i]), v2 = unpack_bf16(a2[i]), v3 = unpack_bf16(a3[i]), v4 = unpack_bf16(a4[i]);
+          const int c = nv * 8 + 2 * i;
+          acc[c] = fmaf(w4, v4.x, fmaf(w3, v3.x, fmaf(w2, v2.x, fmaf(w1, v1.x, acc[c]))));
+          acc[c + 1] = fmaf(w4, v4.y, fmaf(w3, v3.y, fmaf(w2, v2.y, fmaf(w1, v1.y, acc[c + 1]))));
+        }
       }
     }
   }
-  uint4 o;
-  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-  *reinterpret_cast<uint4*>(p.out + item * p.D + part * 8) = o;
+#pragma unroll
+  for (int nv = 0; nv < NV; ++nv) {
+    uint4 o;
+    o.x = pack_bf16(acc[nv * 8 + 0], acc[nv * 8 + 1]); o.y = pack_bf16(acc[nv * 8 + 2], acc[nv * 8 + 3]);
+    o.z = pack_bf16(acc[nv * 8 + 4], acc[nv * 8 + 5]); o.w = pack_bf16(acc[nv * 8 + 6], acc[nv * 8 + 7]);
+    *reinterpret_cast<uint4*>(p.out + item * p.D + part * CPL + nv * 8) = o;
+  }
 }
 
 }  // namespace
@@ -384,9 +393,14 @@ extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes,
   const size_t pj = proj_bf16 ? 2 : 4;
   const bool fast44 = L == 4 && P == 4 && (reinterpret_cast<uintptr_t>(proj) % 16) == 0 && (ldp * pj) % 16 == 0 &&
                       ((size_t)M * 32 * pj) % 16 == 0 && (long)S * M * D < (1l << 30) && !getenv("TAIR_MSDA_GENERIC");
-  if (fast44) {
-    if (proj_bf16) msda_fused44_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
-    else msda_fused44_kernel<float><<<(unsigned)grid, 256, 0, st>>>(p);
+  if (fast44 && D % 16 == 0 && !getenv("TAIR_MSDA_CPL8")) {
+    p.lanes_per_item = D / 16;
+    const long grid16 = (p.items * p.lanes_per_item + 255) / 256;
+    if (proj_bf16) msda_fused44_kernel<__nv_bfloat16, 16><<<(unsigned)grid16, 256, 0, st>>>(p);
+    else msda_fused44_kernel<float, 16><<<(unsigned)grid16, 256, 0, st>>>(p);
+  } else if (fast44) {
+    if (proj_bf16) msda_fused44_kernel<__nv_bfloat16, 8><<<(unsigned)grid, 256, 0, st>>>(p);
+    else msda_fused44_kernel<float, 8><<<(unsigned)grid, 256, 0, st>>>(p);
   } else if (L == 4 && P == 4) {
     if (proj_bf16) msda_fused_kernel<4, 4, __nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
     else msda_fused_kernel<4, 4, float><<<(unsigned)grid, 256, 0, st>>>(p);
