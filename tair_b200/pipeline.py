@@ -94,3 +94,14 @@ def restore_image(lq: np.ndarray, cldm, sampler, *, cond_fn: Optional[Callable] 
     local = torch.cat(decoded, 0) if decoded else torch.zeros((0, 3, 512, 512), device=dev)
     all_tiles = T.gather_tiles(local, n, group)
     return T.merge_patches_with_overlap(all_tiles, lq.shape[:2], 512, 64)
+
+
+def save_image(img: torch.Tensor, path: str) -> None:
+    """(1,3,H,W) or (3,H,W) image in [0,1] -> 8-bit PNG/JPEG (host side; val_patches.py writes the restored image with
+    torchvision's ToPILImage, i.e. mul(255) and a truncating byte cast)."""
+    from PIL import Image
+    t = img.detach()
+    if t.dim() == 4:
+        t = t[0]
+    arr = t.clamp(0, 1).mul(255).byte().permute(1, 2, 0).cpu().numpy()
+    Image.fromarray(arr).save(path)

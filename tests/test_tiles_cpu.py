@@ -92,3 +92,13 @@ def test_bicubic_tables_reproduce_pil_exactly():
     b, c = pil_bicubic_coeffs(128, 512)
     assert b.shape == (512, 2) and c.shape == (512, 5) and (b[:, 1] <= 5).all()
     assert np.abs(c.sum(1) - (1 << 22)).max() <= 3                       # rows sum to 1.0 in 22-bit fixed point
+
+
+def test_save_image_matches_to_pil_semantics(tmp_path):
+    """pipeline.save_image writes what TF.to_pil_image(...).save() writes (val_patches.py:389-390): mul(255), byte cast."""
+    from PIL import Image
+    from tair_b200.pipeline import save_image
+    x = torch.rand((1, 3, 9, 7), generator=torch.Generator().manual_seed(0))
+    p = str(tmp_path / "restored.png")
+    save_image(x, p)
+    assert np.array_equal(np.asarray(Image.open(p)), x[0].mul(255).byte().permute(1, 2, 0).numpy())
