@@ -61,3 +61,23 @@ def merge_tiles(tiles: Sequence[torch.Tensor], original_size: Tuple[int, int], p
             k += 1
     out = canvas / weight.clamp(min=1e-8)
     return out[:, :, :int(oh * scale), :int(ow * scale)]
+
+
+def resize_tile_reference(tile_u8, out_size: int, coeff_fn):
+    """numpy restatement of PIL's two fixed-point resampling passes (Pillow Resample.c: ImagingResampleHorizontal_8bpc
+    then ImagingResampleVertical_8bpc) driven by per-output-index tables ``coeff_fn(in_size, out_size) -> (bounds,
+    coeffs)``; the CPU test pins the product's tables (tair_b200.tiles.pil_bicubic_coeffs) against PIL through it."""
+    import numpy as np
+    h, w = tile_u8.shape[:2]
+    bx, cx = coeff_fn(w, out_size)
+    by, cy = coeff_fn(h, out_size)
+    t = tile_u8.astype(np.int64)
+    tmp = np.zeros((h, out_size, 3), np.int64)
+    for ox in range(out_size):
+        x0, n = bx[ox]
+        tmp[:, ox] = np.clip(((1 << 21) + (t[:, x0:x0 + n] * cx[ox, :n, None].astype(np.int64)).sum(1)) >> 22, 0, 255)
+    out = np.zeros((out_size, out_size, 3), np.int64)
+    for oy in range(out_size):
+        y0, n = by[oy]
+        out[oy] = np.clip(((1 << 21) + (tmp[y0:y0 + n] * cy[oy, :n, None, None].astype(np.int64)).sum(0)) >> 22, 0, 255)
+    return out.astype(np.uint8)

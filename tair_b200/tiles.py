@@ -82,23 +82,6 @@ def pil_bicubic_coeffs(in_size: int, out_size: int):
     return bounds, coeffs
 
 
-def resize_tile_reference(tile_u8: np.ndarray, out_size: int) -> np.ndarray:
-    """numpy restatement of the two fixed-point passes (used by the CPU test to pin the tables against PIL)."""
-    h, w = tile_u8.shape[:2]
-    bx, cx = pil_bicubic_coeffs(w, out_size)
-    by, cy = pil_bicubic_coeffs(h, out_size)
-    t = tile_u8.astype(np.int64)
-    tmp = np.zeros((h, out_size, 3), np.int64)
-    for ox in range(out_size):
-        x0, n = bx[ox]
-        tmp[:, ox] = np.clip(((1 << 21) + (t[:, x0:x0 + n] * cx[ox, :n, None].astype(np.int64)).sum(1)) >> 22, 0, 255)
-    out = np.zeros((out_size, out_size, 3), np.int64)
-    for oy in range(out_size):
-        y0, n = by[oy]
-        out[oy] = np.clip(((1 << 21) + (tmp[y0:y0 + n] * cy[oy, :n, None, None].astype(np.int64)).sum(0)) >> 22, 0, 255)
-    return out.astype(np.uint8)
-
-
 class TileFrontEnd:
     """GPU replacement of split_image_with_overlap + per-tile PIL resize + ToTensor (val_patches.py:25-92,291-294,318):
     the zero-padded LQ image is uploaded once; ``tiles(idx)`` crops and resizes any subset of tiles on the device."""

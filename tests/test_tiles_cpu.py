@@ -77,7 +77,8 @@ def test_bicubic_tables_reproduce_pil_exactly():
     """The host tables behind the GPU tile front-end (tiles.pil_bicubic_coeffs) against PIL itself: the numpy
     restatement of the two fixed-point passes must give PIL's Image.resize(BICUBIC) bytes."""
     from PIL import Image
-    from tair_b200.tiles import pil_bicubic_coeffs, resize_tile_reference
+    from tair_b200.tiles import pil_bicubic_coeffs
+    resize_tile_reference = lambda t, n: OT.resize_tile_reference(t, n, pil_bicubic_coeffs)
     rng = np.random.default_rng(3)
     cases = [rng.integers(0, 256, (128, 128, 3), dtype=np.uint8) for _ in range(2)]
     edge = np.zeros((128, 128, 3), np.uint8)
