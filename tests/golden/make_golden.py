@@ -1,7 +1,7 @@
 """Generate the committed golden fixtures by running the UNMODIFIED reference (imported from /root/reference
 through oracle/ref_harness.py).  Run here (build container) only:
 
-    python tests/golden/make_golden.py [unet] [sched] [msda] [merge] [testr] [manifest]
+    python tests/golden/make_golden.py [unet] [sched] [msda] [merge] [testr] [manifest] [vae] [clip] [tok] [swinir]
 
 The reference has no tests or known-answer vectors of its own for this path, so these fixtures —
 outputs of the reference's own modules on seeded inputs/weights — are what pins the oracle; the GPU box, which has
