@@ -1,0 +1,74 @@
+"""Host-side logic that needs no GPU: character codec and prompt templates (terediff/dataset/utils.py:18-40,
+spaced_sampler.py:298-317), the Instances container (detectron2 structures/instances.py:8-144), the respaced schedule
+tables against the reference fixture, and the GroupNorm-free pieces of the sampler API."""
+import numpy as np
+import pytest
+import torch
+
+from tair_b200 import prompt
+from tair_b200.testr.structures import Instances
+
+
+def test_character_table_and_codec_round_trip():
+    assert len(prompt.CTLABELS) == 95 and prompt.CTLABELS[0] == " " and prompt.CTLABELS[-1] == "~"
+    assert prompt.CTLABELS[33] == "A" and prompt.CTLABELS[65] == "a" and prompt.CTLABELS[16] == "0"
+    for word in ("EXIT", "no-parking", "24/7 OPEN!", "", "x" * 25):
+        idx = prompt.encode(word)
+        assert len(idx) == 25 and all(i == 96 for i in idx[len(word):])
+        assert prompt.decode(idx) == word                      # decode stops at the first pad index
+    assert prompt.decode([33, 34, 200, 35]) == "AB"            # ... or at any index outside the table
+    assert prompt.decode(torch.tensor([40, 41, 96, 96])) == "HI"
+
+
+def test_prompt_templates_match_reference_strings():
+    assert prompt.build_prompt(["EXIT", "24"], "CAPTION") == \
+        'A realistic scene where the texts "EXIT", "24" appear clearly on signs, boards, buildings, or other objects.'
+    assert prompt.build_prompt([], "CAPTION") == \
+        "A realistic scene where the texts  appear clearly on signs, boards, buildings, or other objects."
+    assert prompt.build_prompt(["a", "b"], "TAG") == '"a", "b"'
+    with pytest.raises(ValueError):
+        prompt.build_prompt(["a"], "POEM")
+
+
+def test_decode_texts_batches_instances():
+    a, b = Instances((512, 512)), Instances((512, 512))
+    a.recs = torch.tensor([prompt.encode("STOP"), prompt.encode("go")])
+    a.polygons = torch.arange(64, dtype=torch.float32).view(2, 32) + 0.7
+    b.recs = torch.zeros((0, 25), dtype=torch.long)
+    b.polygons = torch.zeros((0, 32))
+    texts, polys = prompt.decode_texts([a, b])
+    assert texts == [["STOP", "go"], []]
+    assert len(polys[0]) == 2 and polys[0][0].shape == (16, 2) and polys[0][0].dtype == np.int32 and polys[1] == []
+    assert polys[0][1][0, 0] == 32                            # float -> int32 truncation as .astype(np.int32)
+
+
+def test_instances_container_semantics():
+    r = Instances((480, 640))
+    assert r.image_size == (480, 640)
+    with pytest.raises(NotImplementedError):                   # as detectron2: an empty container has no length
+        len(r)
+    r.scores = torch.tensor([0.9, 0.6, 0.8])
+    r.set("recs", torch.zeros((3, 25), dtype=torch.long))
+    assert len(r) == 3 and r.has("scores") and not r.has("polygons")
+    assert set(r.get_fields()) == {"scores", "recs"} and torch.equal(r.get("scores"), r.scores)
+    with pytest.raises(AssertionError):
+        r.polygons = torch.zeros((2, 32))                      # every field must share the instance count
+    with pytest.raises(AttributeError):
+        _ = r.beziers
+
+
+def test_spaced_schedule_matches_reference_fixture(golden):
+    """make_schedule(50) on the CPU: the respaced timestep set and all eight fp32 tables of the reference
+    (spaced_sampler.py:77-121), including the inf at the zero-terminal-SNR end of sqrt_recip*_alphas_cumprod."""
+    from tair_b200.model.gaussian_diffusion import val_diffusion
+    from tair_b200.sampler import SpacedSampler
+    g = golden("schedule_50.npz")
+    s = SpacedSampler(val_diffusion().betas, "v", False)
+    s.make_schedule(50)
+    assert np.array_equal(np.asarray(s.timesteps), g["timesteps"]) and len(s.timesteps) == 50
+    for name in ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                 "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                 "posterior_mean_coef1", "posterior_mean_coef2"):
+        got = getattr(s, name).numpy()
+        assert got.dtype == np.float32 and np.array_equal(got, g[name], equal_nan=True), name
+    assert np.isinf(s.sqrt_recip_alphas_cumprod.numpy()[-1])
