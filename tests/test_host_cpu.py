@@ -72,3 +72,38 @@ def test_spaced_schedule_matches_reference_fixture(golden):
         got = getattr(s, name).numpy()
         assert got.dtype == np.float32 and np.array_equal(got, g[name], equal_nan=True), name
     assert np.isinf(s.sqrt_recip_alphas_cumprod.numpy()[-1])
+
+
+def _shapes(m, skip_suffix=()):
+    return {k: list(v.shape) for k, v in m.state_dict().items() if not k.endswith(tuple(skip_suffix))}
+
+
+def test_state_dict_names_and_shapes_equal_the_reference(manifests):
+    """Checkpoint compatibility without a GPU: every parameter / buffer name and shape of the product modules equals
+    the reference module's (tests/golden/manifests.json was generated from the reference constructors)."""
+    from tair_b200.model import ControlLDM
+    from tair_b200.model.clip import FrozenOpenCLIPEmbedder
+    from tair_b200.model.swinir import SwinIR
+    from tair_b200.model.vae import AutoencoderKL
+    from tair_b200.testr import TransformerDetector, default_cfg
+    u = dict(in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[4, 2, 1], num_res_blocks=2,
+             channel_mult=[1, 2, 4, 4], num_head_channels=64, use_spatial_transformer=True,
+             use_linear_in_transformer=True, transformer_depth=1, context_dim=128, legacy=False)
+    c = dict(u)
+    c.pop("out_channels")
+    c["hint_channels"] = 4
+    m = ControlLDM(u, c)
+    assert _shapes(m.unet) == manifests["unet_narrow"]
+    assert _shapes(m.controlnet) == manifests["controlnet_narrow"]
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    assert _shapes(AutoencoderKL(dd, 4)) == manifests["vae"]
+    clip = FrozenOpenCLIPEmbedder(1024, None, dict(context_length=77, vocab_size=49408, width=1024, heads=16, layers=24),
+                                  layer="penultimate")
+    assert _shapes(clip) == manifests["clip_text"]
+    sw = SwinIR(img_size=64, patch_size=1, in_chans=3, embed_dim=180, depths=[6] * 8, num_heads=[6] * 8, window_size=8,
+                mlp_ratio=2, sf=8, img_range=1.0, upsampler="nearest+conv", resi_connection="1conv", unshuffle=True,
+                unshuffle_scale=8)
+    assert _shapes(sw, ("relative_position_index",)) == manifests["swinir"]
+    det = TransformerDetector(default_cfg("cpu"))
+    assert _shapes(det) == manifests["testr"]
