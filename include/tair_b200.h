@@ -117,13 +117,16 @@ int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, const float*
 int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
                    int32_t M, int32_t C, float eps, void* stream);
 
-/* One ancestral-sampling update (v-parameterisation), all tensors fp32 [B, per_sample]:
- *   v      = v_uncond ? v_uncond + cfg_scale*(v_cond - v_uncond) : v_cond
- *   x0     = sqrt_ac[t]*x - sqrt_1mac[t]*v
+/* One ancestral-sampling update, all tensors fp32 [B, per_sample]:
+ *   v      = v_uncond ? v_uncond + cfg_scale*(v_cond - v_uncond) : v_cond      (cfg_scale_dev, a 1-element DEVICE
+ *            scalar, overrides cfg_scale when non-NULL: a captured CUDA graph then serves every guidance scale)
+ *   x0     = A[t]*x - B[t]*v        v-parameterisation: A = sqrt_alphas_cumprod, B = sqrt_one_minus_alphas_cumprod;
+ *                                   eps-parameterisation: pass A = sqrt_recip_alphas_cumprod, B = sqrt_recipm1_alphas_cumprod
+ *                                   (spaced_sampler.py:133-147)
  *   x_prev = coef1[t]*x0 + coef2[t]*x + (t != 0) * sqrt(post_var[t]) * noise
  * t is the int64 [B] index into the respaced schedule tables (device pointers).  pred_x0 may be NULL. */
 int tair_sampler_update(const float* x, const float* v_cond, const float* v_uncond, float cfg_scale,
-                        const float* noise, float* x_prev, float* pred_x0, const int64_t* t,
+                        const float* cfg_scale_dev, const float* noise, float* x_prev, float* pred_x0, const int64_t* t,
                         const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
                         const float* posterior_mean_coef1, const float* posterior_mean_coef2,
                         const float* posterior_variance, int32_t B, int32_t per_sample, void* stream);
@@ -196,13 +199,6 @@ int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int6
                     const void* proj, int64_t ldp, int32_t proj_bf16, const float* ref, int32_t ref_dim,
                     int64_t ref_batch_stride, int32_t q_per_ref, void* out, int32_t B, int32_t S, int32_t M,
                     int32_t D, int32_t L, int32_t Lq, int32_t P, void* stream);
-
-/* Short-sequence multi-head attention (nn.MultiheadAttention core, head_dim 32, L <= 128) on the fused in_proj
- * output qkv [rows, ld] (q | k | v, each H*32 wide); sequence (o, i), o < n_outer, i < n_inner, starts at row
- * o*outer_stride + i*inner_stride and its tokens are tok_stride rows apart.  out [rows, ldo] uses the same rows. */
-int tair_mha_small(const void* qkv, int64_t ld, void* out, int64_t ldo, int32_t H, int32_t head_dim, int32_t L,
-                   int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride, int64_t tok_stride,
-                   float scale, void* stream);
 
 /* Self-attention over many short strided sequences (head slots of 64 columns; narrower heads are zero-padded by the
  * caller): q/k/v are column offsets into one row-major [rows, ld] bf16 matrix (fused in_proj output); sequence (o, i),

@@ -96,10 +96,11 @@ def tables_to_torch(sched: Dict[str, np.ndarray], device="cpu") -> Dict[str, tor
     return {k: torch.tensor(v, dtype=torch.float32, device=device) for k, v in sched.items() if k != "timesteps"}
 
 
-def sample_loop(model_fn, sched: Dict[str, np.ndarray], x_T: torch.Tensor, noises, cond_fn=None):
+def sample_loop(model_fn, sched: Dict[str, np.ndarray], x_T: torch.Tensor, noises, cond_fn=None, trace=None):
     """val_sample / sample loop skeleton — spaced_sampler.py:270-296: model_t = original timestep, t = 49..0 index;
     ``noises[i]`` replaces torch.randn_like at loop iteration i (noise injection for parity).
-    ``model_fn(x, model_t) -> (v, feats)``;  ``cond_fn(i, feats)`` is called after each step (TESTR/prompt feedback)."""
+    ``model_fn(x, model_t) -> (v, feats)``;  ``cond_fn(i, feats)`` is called after each step (TESTR/prompt feedback);
+    ``trace`` (a list) receives the latent after every step."""
     tabs = tables_to_torch(sched, x_T.device)
     ts = np.flip(sched["timesteps"])
     total = len(ts)
@@ -110,6 +111,8 @@ def sample_loop(model_fn, sched: Dict[str, np.ndarray], x_T: torch.Tensor, noise
         t = torch.full((B,), total - i - 1, device=x.device, dtype=torch.long)
         v, feats = model_fn(x, model_t)
         x, _ = p_sample_update(tabs, x, v, t, noises[i])
+        if trace is not None:
+            trace.append(x)
         if cond_fn is not None:
             cond_fn(i, feats)
     return x

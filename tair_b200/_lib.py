@@ -57,7 +57,7 @@ SIGNATURES = {
     "tair_groupnorm_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "tair_groupnorm_nhwc": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),
     "tair_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _f32, _vp]),
-    "tair_sampler_update": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "tair_sampler_update": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "tair_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "tair_nchw_to_nhwc_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tair_nhwc_to_nchw_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp]),
@@ -72,7 +72,6 @@ SIGNATURES = {
     "tair_tiles_bicubic_u8": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "tair_blend_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_msda_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "tair_mha_small": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i64, _i32, _i64, _i64, _i64, _f32, _vp]),
     "tair_attention_seq_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _i32, _i64, _i64, _i64, _f32, _vp]),
     "tair_softmax_rows_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp]),
     "tair_transpose_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
@@ -84,11 +83,15 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        # the stamp of the prebuilt library must match the sources on disk; a stale or missing library is rebuilt
+        # in-tree (nvcc cross-compiles sm_100a) — and if that is impossible the call fails: there is no fallback
+        try:
+            from . import build as _build
+            _build.ensure()
+        except Exception as e:
             raise TairLibraryError(
-                f"{LIB_PATH} not found: build it with `python -m tair_b200.build` "
-                "(tair_b200 has no CPU / PyTorch fallback)"
-            )
+                f"{LIB_PATH} is missing or stale and could not be rebuilt ({e}); build it with "
+                "`python -m tair_b200.build` (tair_b200 has no CPU / PyTorch fallback)") from e
         try:
             handle = C.CDLL(LIB_PATH)
         except OSError as e:  # pragma: no cover

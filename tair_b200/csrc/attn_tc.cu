@@ -381,11 +381,7 @@ int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   if ((rc = make_map(&tmQ, q, ldq, H * 64, Lq, n_inner, n_outer, q_tok, q_inner, q_outer))) return rc;
   if ((rc = make_map(&tmK, k, ldk, H * 64, Lk, n_inner, n_outer, kv_tok, kv_inner, kv_outer))) return rc;
   if ((rc = make_map(&tmV, v, ldv, H * 64, Lk, n_inner, n_outer, kv_tok, kv_inner, kv_outer))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAIR_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
-    attr_set = true;
-  }
+  TAIR_SMEM_OPTIN(attn_tc_kernel, AT_SMEM);
   const long grid = (long)n_outer * n_inner * H * p.q_tiles;
   TAIR_REQUIRE(grid < (1l << 31), "attention: grid too large");
   attn_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);

@@ -39,6 +39,20 @@ int check_launch(const char* what);  // cudaGetLastError -> code
 
 int num_sms();
 
+// Opt a kernel in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute is PER DEVICE, so the "already done" flag
+// is kept per device ordinal (a process driving several GPUs would otherwise fail its first large-smem launch on the
+// second device).  The static lives in the enclosing function, i.e. once per kernel template instantiation.
+#define TAIR_SMEM_OPTIN(kernel, bytes)                                                                      \
+  do {                                                                                                      \
+    static bool done__[64] = {};                                                                            \
+    int dev__ = 0;                                                                                          \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ < 0 || dev__ >= 64) dev__ = 0;                        \
+    if (!done__[dev__]) {                                                                                   \
+      TAIR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      done__[dev__] = true;                                                                                 \
+    }                                                                                                       \
+  } while (0)
+
 // TMA descriptor construction through the driver entry point (no -lcuda).
 // dims/strides follow cuTensorMapEncodeTiled: dim[0] is the contiguous one,
 // strides are BYTES for dims 1..rank-1.

@@ -22,7 +22,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       const int64_t* __restrict__ t, const float* __restrict__ sqrt_ac,
                                       const float* __restrict__ sqrt_1mac, const float* __restrict__ coef1,
                                       const float* __restrict__ coef2, const float* __restrict__ post_var,
-                                      float cfg_scale, int per_sample, int total) {
+                                      float cfg_scale, const float* __restrict__ cfg_scale_dev, int per_sample,
+                                      int total) {
   // 4 elements per thread; per_sample % 4 == 0 so a float4 never straddles two samples
   const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= total) return;
@@ -33,6 +34,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
   const float4 xv = *reinterpret_cast<const float4*>(x + i4);
   float4 vv = *reinterpret_cast<const float4*>(v_cond + i4);
   if (v_uncond != nullptr) {
+    if (cfg_scale_dev != nullptr) cfg_scale = *cfg_scale_dev;  // device scalar: one captured graph, any scale
     const float4 vu = *reinterpret_cast<const float4*>(v_uncond + i4);
     vv.x = __fadd_rn(vu.x, __fmul_rn(cfg_scale, __fsub_rn(vv.x, vu.x)));
     vv.y = __fadd_rn(vu.y, __fmul_rn(cfg_scale, __fsub_rn(vv.y, vu.y)));
@@ -230,7 +232,8 @@ using namespace tair;
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
 
 extern "C" int tair_sampler_update(const float* x, const float* v_cond, const float* v_uncond, float cfg_scale,
-                                   const float* noise, float* x_prev, float* pred_x0, const int64_t* t,
+                                   const float* cfg_scale_dev, const float* noise, float* x_prev, float* pred_x0,
+                                   const int64_t* t,
                                    const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
                                    const float* posterior_mean_coef1, const float* posterior_mean_coef2,
                                    const float* posterior_variance, int32_t B, int32_t per_sample, void* stream) {
@@ -244,7 +247,7 @@ extern "C" int tair_sampler_update(const float* x, const float* v_cond, const fl
   const int threads = 256, grid = (total / 4 + threads - 1) / threads;
   sampler_update_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       x, v_cond, v_uncond, noise, x_prev, pred_x0, t, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod,
-      posterior_mean_coef1, posterior_mean_coef2, posterior_variance, cfg_scale, per_sample, total);
+      posterior_mean_coef1, posterior_mean_coef2, posterior_variance, cfg_scale, cfg_scale_dev, per_sample, total);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("sampler_update_kernel");
 }

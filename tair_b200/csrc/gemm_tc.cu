@@ -774,12 +774,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BN>
 int launch_bn2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
                const GemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)Cfg2<BN>::SMEM_BYTES));
-    attr_set = true;
-  }
+  TAIR_SMEM_OPTIN(gemm_tc2_kernel<BN>, Cfg2<BN>::SMEM_BYTES);
   const int tiles2 = ((p.tiles_m + 1) / 2) * p.tiles_n;
   int pairs = num_sms() / 2;
   if (tiles2 < pairs) pairs = tiles2;
@@ -791,12 +786,7 @@ int launch_bn2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
 template <int BN>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
               const GemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)Cfg<BN>::SMEM_BYTES));
-    attr_set = true;
-  }
+  TAIR_SMEM_OPTIN(gemm_tc_kernel<BN>, Cfg<BN>::SMEM_BYTES);
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC64, tmC32, p);

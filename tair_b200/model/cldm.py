@@ -53,6 +53,65 @@ class ControlLDM(nn.Module):
             s = self._side[device] = torch.cuda.Stream(device=device)
         return s
 
+    # -- checkpoint loading (host-side key mapping; cldm.py:33-90) -----------------------------------
+    @torch.no_grad()
+    def load_pretrained_sd(self, sd: Dict[str, torch.Tensor]):
+        """cldm.py:33-61: pick ``model.diffusion_model.*`` / ``first_stage_model.*`` / ``cond_stage_model.*`` out of a
+        Stable Diffusion 2.1 checkpoint -> (unused, missing) key sets; the three modules are frozen in eval mode."""
+        module_map = {"unet": "model.diffusion_model", "vae": "first_stage_model", "clip": "cond_stage_model"}
+        used, missing = set(), set()
+        mods = [(n, getattr(self, n)) for n in ("unet", "vae", "clip") if isinstance(getattr(self, n), nn.Module)]
+        for name, module in mods:
+            init_sd = {}
+            for key in module.state_dict():
+                target = ".".join([module_map[name], key])
+                if target not in sd:
+                    missing.add(target)
+                    continue
+                init_sd[key] = sd[target].clone()
+                used.add(target)
+            module.load_state_dict(init_sd, strict=False)
+        for _, module in mods:
+            module.eval()
+            module.train = lambda mode=True, _m=module: _m      # disabled_train (cldm.py:14-17)
+            for p in module.parameters():
+                p.requires_grad = False
+        return set(sd.keys()) - used, missing
+
+    @torch.no_grad()
+    def load_controlnet_from_ckpt(self, sd: Dict[str, torch.Tensor]) -> None:
+        """cldm.py:63-65."""
+        self.controlnet.load_state_dict(sd, strict=True)
+
+    @torch.no_grad()
+    def load_controlnet_from_unet(self):
+        """cldm.py:67-90: initialise the ControlNet from the UNet encoder; the 8-channel input conv gets the UNet's
+        4 input channels plus zeros -> (keys widened with zeros, keys kept from scratch)."""
+        unet_sd, scratch = self.unet.state_dict(), self.controlnet.state_dict()
+        init_sd, widened, kept = {}, set(), set()
+        for key, this in scratch.items():
+            if key in unet_sd:
+                target = unet_sd[key]
+                if this.size() == target.size():
+                    init_sd[key] = target.clone()
+                else:
+                    oc, _, h, w = this.size()
+                    zeros = torch.zeros((oc, this.size(1) - target.size(1), h, w), dtype=target.dtype, device=target.device)
+                    init_sd[key] = torch.cat((target, zeros), dim=1)
+                    widened.add(key)
+            else:
+                init_sd[key] = this.clone()
+                kept.add(key)
+        self.controlnet.load_state_dict(init_sd, strict=True)
+        return widened, kept
+
+    def cast_dtype(self, dtype: torch.dtype) -> "ControlLDM":
+        """cldm.py:181-217 switches the reference's blocks to fp16.  The kernels here always compute in bf16 with fp32
+        accumulation and keep fp32 master parameters, so there is nothing to convert; kept for API compatibility."""
+        self.unet.dtype = dtype
+        self.controlnet.dtype = dtype
+        return self
+
     # -- optional non-hot-path submodules ---------------------------------------------------------
     def attach_vae(self, vae: nn.Module) -> None:
         self.vae = vae

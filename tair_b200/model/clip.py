@@ -96,11 +96,12 @@ class FrozenOpenCLIPEmbedder(nn.Module):
         self.layer_idx = 0 if layer == "last" else 1
         self._tokenizer: Optional[Callable] = None
         self._cache: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self._cache_stamp = None
         self.cache_size = 1024
         # ~190 launches of mostly tiny kernels: launch-bound when run eagerly (3.8 ms for one prompt vs 0.4 ms replayed),
         # so the transformer is captured once per batch size and replayed
         self.use_cuda_graph = True
-        self._graphs = {}
+        self._graphs: "OrderedDict[tuple, tuple]" = OrderedDict()
 
     def attach_tokenizer(self, fn: Callable[[List[str]], torch.Tensor]) -> None:
         self._tokenizer = fn
@@ -110,16 +111,26 @@ class FrozenOpenCLIPEmbedder(nn.Module):
         """Drop memoised prompt embeddings (call after loading new weights)."""
         self._cache.clear()
 
+    def _weight_stamp(self) -> tuple:
+        """Changes whenever any parameter is modified in place (``_version``), re-allocated (``data_ptr``: load into a new
+        module, ``.to()``) or cast: keys both the captured graphs and the memoised prompt embeddings."""
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in self.model.parameters())
+
+    # new prompts per step vary between 1 and the tile batch: pad the batch to a few bucket sizes so that at most
+    # len(_BUCKETS) graphs exist per weight stamp instead of one per distinct count
+    _BUCKETS = (1, 2, 4, 8, 16, 32, 64)
+
     @torch.no_grad()
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:
         if not (self.use_cuda_graph and tokens.is_cuda) or torch.cuda.is_current_stream_capturing():
             return self.encode_with_transformer(tokens)
-        key = (tuple(tokens.shape), tokens.device, self.model.ln_final.weight._version,
-               self.model.token_embedding.weight._version, self.model.token_embedding.weight.data_ptr())
-        entry = self._graphs.get(key)
+        n = tokens.shape[0]
+        nb = next((b for b in self._BUCKETS if b >= n), n)
+        key = (nb, tokens.shape[1], tokens.device, self._weight_stamp())
+        entry = self._graphs.pop(key, None)
         if entry is None:
-            buf = tokens.clone()
-            side = torch.cuda.Stream()
+            buf = tokens.new_zeros((nb, tokens.shape[1]))
+            side = self._side = getattr(self, "_side", None) or torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):   # warm-up outside capture: weight packing, tile tuning, allocator
                 for _ in range(2):
@@ -128,13 +139,14 @@ class FrozenOpenCLIPEmbedder(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self.encode_with_transformer(buf)
-            if len(self._graphs) >= 8:
+            while len(self._graphs) >= 8:                       # least recently used first
                 self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[key] = (g, buf, out)
+            entry = (g, buf, out)
+        self._graphs[key] = entry                               # (re-)insert at the most-recently-used end
         g, buf, out = entry
-        buf.copy_(tokens)
+        buf[:n].copy_(tokens)
         g.replay()
-        return out.clone()
+        return out[:n].clone()
 
     @torch.no_grad()
     def encode_with_transformer(self, text: torch.Tensor) -> torch.Tensor:
@@ -163,6 +175,10 @@ class FrozenOpenCLIPEmbedder(nn.Module):
                                    "merge table or call attach_tokenizer(fn) with a List[str] -> LongTensor[B,77] callable")
         if isinstance(text, str):
             text = [text]
+        stamp = self._weight_stamp()
+        if stamp != self._cache_stamp:      # weights changed (load_state_dict / .to() / cast): drop stale embeddings
+            self._cache.clear()
+            self._cache_stamp = stamp
         new = [t for t in dict.fromkeys(text) if t not in self._cache]
         if new:
             z = self(self._tokenizer(new).to(self.model.positional_embedding.device))

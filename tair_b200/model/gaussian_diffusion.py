@@ -44,6 +44,24 @@ class Diffusion:
         if zero_snr:
             betas = enforce_zero_terminal_snr(betas)
         self.betas = betas
+        abar = np.cumprod(1.0 - betas, axis=0)
+        self.sqrt_alphas_cumprod = np.sqrt(abar).astype(np.float32)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - abar).astype(np.float32)
+
+    def q_sample(self, z_0, t, noise):
+        """gaussian_diffusion.py:124-129 (forward diffusion; used by the legacy pipeline's start point / noise_aug)."""
+        import torch
+        a = torch.as_tensor(self.sqrt_alphas_cumprod, device=z_0.device)[t].view(-1, *([1] * (z_0.dim() - 1)))
+        b = torch.as_tensor(self.sqrt_one_minus_alphas_cumprod, device=z_0.device)[t].view(-1, *([1] * (z_0.dim() - 1)))
+        return a * z_0 + b * noise
+
+    # the reference Diffusion is an nn.Module whose buffers are only used by the training loss; inference code calls
+    # ``diffusion.to(device)`` (val_patches.py:240) and reads ``.betas`` (numpy) — keep both working
+    def to(self, *args, **kwargs) -> "Diffusion":
+        return self
+
+    def eval(self) -> "Diffusion":
+        return self
 
 
 def val_diffusion() -> Diffusion:

@@ -269,7 +269,7 @@ class SwinIR(nn.Module):
                 else:
                     tb = blk["bias"].unsqueeze(0).contiguous()
                 qkv = ops.gemm(ops.layernorm_ragged(xw, *blk["n1"], C), blk["qkv"][0], bias=blk["qkv"][1])
-                a = ops.attention_windows(qkv, n_heads=H, L=N, n_windows=nwin, scale=scale, bias=tb)
+                a = ops.attention_windows(qkv, n_heads=H, L=N, n_windows=nwin, scale=scale, bias=tb, real_head_dim=C // H)
                 xw = ops.gemm(a, blk["proj"][0], bias=blk["proj"][1], residual=xw)
                 hmid = ops.gemm(ops.layernorm_ragged(xw, *blk["n2"], C), blk["fc1"][0], bias=blk["fc1"][1], act=ops.ACT_GELU)
                 r = ops.gemm(hmid, blk["fc2"][0], bias=blk["fc2"][1], residual=xw)

@@ -91,7 +91,7 @@ class Conv3x3(nn.Conv2d, _PackMixin):
     def forward(self, x: torch.Tensor, *, residual=None, rowgroup=None, rows_per_group=0, out=None, out_dtype=BF16):
         w, b = self.packed()
         return ops.conv3x3(x, w, stride=self.stride[0], pad=self.pad_lo, bias=b, residual=residual, rowgroup=rowgroup,
-                           rows_per_group=rows_per_group, out=out, out_dtype=out_dtype)
+                           rows_per_group=rows_per_group, out=out, out_dtype=out_dtype, real_cin=self.in_channels)
 
 
 class GroupNorm(nn.GroupNorm, _PackMixin):

@@ -165,9 +165,10 @@ def _splitk_workspace(device, need: int) -> torch.Tensor:
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad: int = 1, bias=None, residual=None,
             rowgroup=None, rows_per_group=0, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
-            out_dtype=BF16) -> torch.Tensor:
+            out_dtype=BF16, real_cin: Optional[int] = None) -> torch.Tensor:
     """3x3 convolution on channels-last bf16: x [B,H,W,Cin], w [Cout, 9*Cin] -> [B,Ho,Wo,Cout].
-    pad=1: PyTorch padding=1; pad=0: zero row/column on the bottom/right only (VAE downsampler)."""
+    pad=1: PyTorch padding=1; pad=0: zero row/column on the bottom/right only (VAE downsampler).
+    ``real_cin``: the layer's true input channels when x is zero-padded to the 64-channel k-block (work accounting only)."""
     _cuda(x, "x", BF16), _cuda(w, "w", BF16)
     if x.dim() != 4 or not x.is_contiguous():
         raise TairError("conv3x3: x must be a contiguous [B,H,W,C] tensor")
@@ -187,7 +188,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad: int = 1, 
         # (too few 128-row tiles to fill the SMs otherwise); see tair_epilogue.workspace in include/tair_b200.h
         ws = _splitk_workspace(x.device, 3 * M * Cout * 4)
         e.workspace, e.workspace_bytes = ws.data_ptr(), ws.numel()
-    with _timed("conv3x3", 2.0 * M * Cout * 9 * Cin, (B, H, W, Cin, Cout, stride)):
+    with _timed("conv3x3", 2.0 * M * Cout * 9 * (real_cin or Cin), (B, H, W, Cin, Cout, stride)):
         rc = _lib.lib().tair_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, stride, pad, C.byref(e), _stream())
     _lib.check(rc, "tair_conv3x3_bf16")
     return out
@@ -276,22 +277,34 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     return out
 
 
-def sampler_update(x, v_cond, noise, t, tables, *, v_uncond=None, cfg_scale: float = 1.0, out=None, pred_x0=None):
-    """tables = (sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
-    posterior_variance): fp32 CUDA vectors; t int64 [B]."""
-    for tt, n in ((x, "x"), (v_cond, "v"), (noise, "noise")):
+def sampler_update(x, v_cond, noise, t, tables, *, v_uncond=None, cfg_scale: float = 1.0, cfg_scale_dev=None, out=None,
+                   pred_x0=None):
+    """tables = (A, B, posterior_mean_coef1, posterior_mean_coef2, posterior_variance) with x0 = A[t] x - B[t] v:
+    fp32 CUDA vectors; t int64 [B].  ``cfg_scale_dev``: optional 1-element fp32 CUDA tensor overriding ``cfg_scale``."""
+    def chk(tt, n):
         _cuda(tt, n, torch.float32)
-        if not tt.is_contiguous():
-            raise TairError(f"sampler_update: {n} must be contiguous")
+        if not tt.is_contiguous() or tt.shape != x.shape or tt.device != x.device:
+            raise TairError(f"sampler_update: {n} must be a contiguous fp32 tensor of x's shape on x's device")
+        return tt
+    _cuda(x, "x", torch.float32)
+    for tt, n in ((x, "x"), (v_cond, "v"), (noise, "noise")):
+        chk(tt, n)
+    for tt, n in ((v_uncond, "v_uncond"), (out, "out"), (pred_x0, "pred_x0")):
+        if tt is not None:
+            chk(tt, n)
     _cuda(t, "t", torch.int64)
+    if cfg_scale_dev is not None:
+        _cuda(cfg_scale_dev, "cfg_scale_dev", torch.float32)
     B = x.shape[0]
+    if t.numel() != B or not t.is_contiguous():
+        raise TairError("sampler_update: t must be a contiguous int64 vector with one entry per sample")
     per = x.numel() // B
     if out is None:
         out = torch.empty_like(x)
     tabs = [_cuda(tb, "schedule table", torch.float32).data_ptr() for tb in tables]
     rc = _lib.lib().tair_sampler_update(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond), float(cfg_scale),
-                                        noise.data_ptr(), out.data_ptr(), _ptr(pred_x0), t.data_ptr(), *tabs, B, per,
-                                        _stream())
+                                        _ptr(cfg_scale_dev), noise.data_ptr(), out.data_ptr(), _ptr(pred_x0),
+                                        t.data_ptr(), *tabs, B, per, _stream())
     _lib.check(rc, "tair_sampler_update")
     return out
 
@@ -433,25 +446,9 @@ def msda_fused(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_in
     return out
 
 
-def mha_small(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_inner: int, outer_stride: int,
-              inner_stride: int, tok_stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """qkv bf16 [rows, 3*E] fused in_proj output; returns the attention output [rows, E] in the same row order."""
-    _cuda(qkv, "qkv", BF16)
-    q2, ld = _rows(qkv, "qkv")
-    E = q2.shape[1] // 3
-    hd = E // n_heads
-    if out is None:
-        out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
-    o2, ldo = _rows(out, "out")
-    with _timed("mha_small", 4.0 * n_outer * n_inner * n_heads * L * L * hd):
-        rc = _lib.lib().tair_mha_small(q2.data_ptr(), ld, o2.data_ptr(), ldo, n_heads, hd, L, n_outer, n_inner,
-                                       outer_stride, inner_stride, tok_stride, float(hd ** -0.5), _stream())
-    _lib.check(rc, "tair_mha_small")
-    return out
-
-
 def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_inner: int, outer_stride: int,
-                  inner_stride: int, tok_stride: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  inner_stride: int, tok_stride: int, scale: float, out: Optional[torch.Tensor] = None,
+                  real_head_dim: int = 64) -> torch.Tensor:
     """Self-attention over many short strided sequences on the tcgen05 flash kernel.  qkv bf16 [rows, 3*H*64]
     (q | k | v, 64-column head slots, narrower heads zero-padded); returns [rows, H*64] in the same row order."""
     _cuda(qkv, "qkv", BF16)
@@ -463,7 +460,8 @@ def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_in
         out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
     o2, ldo = _rows(out, "out")
     base = q2.data_ptr()
-    with _timed("attention_seq", 4.0 * n_outer * n_inner * n_heads * L * L * 64, (n_outer, n_inner, n_heads, L)):
+    # algorithmic FLOPs count the real head width, not the zero-padded 64-column slot
+    with _timed("attention_seq", 4.0 * n_outer * n_inner * n_heads * L * L * real_head_dim, (n_outer, n_inner, n_heads, L)):
         rc = _lib.lib().tair_attention_seq_bf16(base, base + 2 * E, base + 4 * E, ld, o2.data_ptr(), ldo, n_heads, L,
                                                 n_outer, n_inner, outer_stride, inner_stride, tok_stride, float(scale),
                                                 _stream())
@@ -491,7 +489,8 @@ def tiles_bicubic(image_u8: torch.Tensor, origins: torch.Tensor, bounds: torch.T
 
 
 def attention_windows(qkv: torch.Tensor, *, n_heads: int, L: int, n_windows: int, scale: float,
-                      bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      real_head_dim: int = 64) -> torch.Tensor:
     """Swin window attention: qkv bf16 [n_windows*L, 3*H*64] (q | k | v, 64-column head slots); bias fp32
     [nw, H, L(key), L(query)] = (relative-position bias + mask) / scale, window w uses table w % nw."""
     _cuda(qkv, "qkv", BF16)
@@ -509,7 +508,7 @@ def attention_windows(qkv: torch.Tensor, *, n_heads: int, L: int, n_windows: int
         out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
     o2, ldo = _rows(out, "out")
     base = q2.data_ptr()
-    with _timed("attention_windows", 4.0 * n_windows * n_heads * L * L * 64, (n_windows, n_heads, L)):
+    with _timed("attention_windows", 4.0 * n_windows * n_heads * L * L * real_head_dim, (n_windows, n_heads, L)):
         rc = _lib.lib().tair_attention_windows_bf16(base, base + 2 * E, base + 4 * E, ld, o2.data_ptr(), ldo, n_heads, L,
                                                     n_windows, None if bias is None else bias.data_ptr(), nw, float(scale),
                                                     _stream())

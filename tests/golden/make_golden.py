@@ -1,7 +1,7 @@
 """Generate the committed golden fixtures by running the UNMODIFIED reference (imported from /root/reference
 through oracle/ref_harness.py).  Run here (build container) only:
 
-    python tests/golden/make_golden.py [unet] [sched] [msda] [merge] [testr] [manifest] [vae] [clip] [tok] [swinir]
+    python tests/golden/make_golden.py [unet] [sched] [msda] [merge] [testr] [manifest] [vae] [clip] [tok] [swinir] [feedback]
 
 The reference has no tests or known-answer vectors of its own for this path, so these fixtures —
 outputs of the reference's own modules on seeded inputs/weights — are what pins the oracle; the GPU box, which has
@@ -202,6 +202,57 @@ def gen_swinir():
     print("swinir: y std", y.std().item(), "keys", len(man))
 
 
+def gen_feedback():
+    """val_sample with the text-spotting feedback loop (spaced_sampler.py:246-328), run through the UNMODIFIED reference:
+    its ControlLDM.forward over the full-size ControlledUnetModel + ControlNet, its TransformerDetector and its
+    SpacedSampler.val_sample; 3 steps, batch 1, injected noise, HashClip stand-in for the frozen text encoder."""
+    H.install()
+    from types import SimpleNamespace
+    from terediff.model.cldm import ControlLDM
+    from terediff.model.gaussian_diffusion import enforce_zero_terminal_snr, make_beta_schedule
+    from terediff.sampler.spaced_sampler import SpacedSampler
+    from oracle.val_loop import HashClip
+    mf = json.load(open(os.path.join(HERE, "manifests.json")))
+    u, c = H.build_unet(), H.build_controlnet()
+    u.load_state_dict(Wt.seeded_state_dict(mf["unet_full"]))
+    c.load_state_dict(Wt.seeded_state_dict(mf["controlnet_full"]))
+    ts = H.build_testr()
+    ts.load_state_dict(Wt.seeded_state_dict(mf["testr"]), strict=False)
+    cldm = ControlLDM.__new__(ControlLDM)          # the reference forward() without building the 438 M-parameter VAE/CLIP
+    torch.nn.Module.__init__(cldm)
+    cldm.unet, cldm.controlnet, cldm.control_scales, cldm.clip = u, c, [1.0] * 13, HashClip()
+    betas = enforce_zero_terminal_snr(make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.0120))
+    s = SpacedSampler(betas, "v", False)
+    steps = 3
+    x_T, c_img = seeded((1, 4, 64, 64), 9800), seeded((1, 4, 64, 64), 9900)
+    noises = [seeded((1, 4, 64, 64), 10000 + i) for i in range(steps)]
+    cond = dict(c_txt=cldm.clip.encode(""), c_img=c_img)
+    cfg = SimpleNamespace(exp_args=SimpleNamespace(mode="VAL", prompt_style="CAPTION"))
+    it = iter(noises)
+    xs = []
+    orig = torch.randn_like
+    orig_p = s.p_sample
+
+    def p_sample(*a, **k):
+        out = orig_p(*a, **k)
+        xs.append(out[0].clone())
+        return out
+    s.p_sample = p_sample
+    torch.randn_like = lambda _x: next(it)
+    try:
+        with torch.no_grad():
+            x, res = s.val_sample(cldm, "cpu", steps, (1, 4, 64, 64), cond, None, 1.0, x_T=x_T, progress=False, cfg=cfg,
+                                  pure_cldm=cldm, ts_model=ts)
+    finally:
+        torch.randn_like = orig
+    np.savez_compressed(os.path.join(HERE, "val_feedback.npz"), x=torch.cat(xs).numpy(),
+                        **{f"polys{i}": np.stack(r["pred_polys"]) if r["pred_polys"] else np.zeros((0, 16, 2), np.int32)
+                           for i, r in enumerate(res)})
+    json.dump({"steps": steps, "timesteps": [int(r["timestep"]) for r in res], "pred_texts": [r["pred_texts"] for r in res],
+               "pred_prompt": [r["pred_prompt"] for r in res]}, open(os.path.join(HERE, "val_feedback.json"), "w"), indent=1)
+    print("val_feedback:", [(int(r["timestep"]), len(r["pred_texts"])) for r in res], "x std", x.std().item())
+
+
 TOKENIZER_CASES = ["", "A realistic scene where the texts \"HELLO\", \"world\" appear clearly on signs.",
                    "it's  a  test &amp;amp; more!!!  123 4.5", "na\u00efve caf\u00e9 \u2014 \u65e5\u672c\u8a9e", "x" * 400,
                    "<start_of_text> hi <end_of_text>", "don't we'll I'm they've you'd HE'S", "  \t\n  ",
@@ -226,4 +277,4 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     for w in what:
         {"manifest": gen_manifest, "unet": gen_unet, "sched": gen_sched, "msda": gen_msda, "merge": gen_merge,
-         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip, "tok": gen_tok, "swinir": gen_swinir}[w]()
+         "testr": gen_testr, "vae": gen_vae, "clip": gen_clip, "tok": gen_tok, "swinir": gen_swinir, "feedback": gen_feedback}[w]()

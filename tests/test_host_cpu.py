@@ -107,3 +107,104 @@ def test_state_dict_names_and_shapes_equal_the_reference(manifests):
     assert _shapes(sw, ("relative_position_index",)) == manifests["swinir"]
     det = TransformerDetector(default_cfg("cpu"))
     assert _shapes(det) == manifests["testr"]
+
+
+def test_checkpoint_loading_surface_of_controlldm():
+    """cldm.py:33-90: load_pretrained_sd maps the SD-2.1 prefixes, load_controlnet_from_unet widens the 8-channel input
+    conv with zeros, load_controlnet_from_ckpt is strict; Diffusion.to() is a no-op like val_patches.py:240 expects."""
+    import torch
+    from tair_b200.model import ControlLDM
+    from tair_b200.model.gaussian_diffusion import val_diffusion
+    u = dict(in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[4, 2, 1], num_res_blocks=1,
+             channel_mult=[1, 2], num_head_channels=32, use_spatial_transformer=True, use_linear_in_transformer=True,
+             transformer_depth=1, context_dim=64, legacy=False)
+    c = dict(u)
+    c.pop("out_channels")
+    c["hint_channels"] = 4
+    m = ControlLDM(u, c)
+    g = torch.Generator().manual_seed(0)
+    ckpt = {"model.diffusion_model." + k: torch.randn(v.shape, generator=g) for k, v in m.unet.state_dict().items()}
+    ckpt["cond_stage_model.unrelated"] = torch.zeros(1)
+    some = next(iter(m.unet.state_dict()))
+    del ckpt["model.diffusion_model." + some]
+    unused, missing = m.load_pretrained_sd(ckpt)
+    assert unused == {"cond_stage_model.unrelated"} and missing == {"model.diffusion_model." + some}
+    for k, v in m.unet.state_dict().items():
+        if k != some:
+            assert torch.equal(v, ckpt["model.diffusion_model." + k])
+    assert not any(p.requires_grad for p in m.unet.parameters()) and m.unet.train() is m.unet and not m.unet.training
+    widened, kept = m.load_controlnet_from_unet()
+    assert widened == {"input_blocks.0.0.weight"}
+    w = m.controlnet.state_dict()["input_blocks.0.0.weight"]
+    assert w.shape[1] == 8 and torch.equal(w[:, :4], m.unet.state_dict()["input_blocks.0.0.weight"]) and (w[:, 4:] == 0).all()
+    assert all(k.startswith(("zero_convs", "middle_block_out")) for k in kept)
+    sd = {k: torch.randn(v.shape, generator=g) for k, v in m.controlnet.state_dict().items()}
+    m.load_controlnet_from_ckpt(sd)
+    assert all(torch.equal(v, sd[k]) for k, v in m.controlnet.state_dict().items())
+    import pytest
+    with pytest.raises(RuntimeError):
+        m.load_controlnet_from_ckpt({k: v for k, v in list(sd.items())[1:]})
+    d = val_diffusion()
+    assert d.to("cpu") is d and len(d.betas) == 1000
+    assert m.cast_dtype(torch.float16) is m
+
+
+def test_sampler_parameterisations_and_graph_key():
+    """'eps' selects the recip tables (spaced_sampler.py:133-139,176-179); unknown names raise; the graph key follows
+    the step count (tables are re-allocated when it changes)."""
+    import pytest
+    from tair_b200.model.gaussian_diffusion import val_diffusion
+    from tair_b200.sampler import SpacedSampler
+    s = SpacedSampler(val_diffusion().betas, "eps", False)
+    s.make_schedule(10)
+    assert s._tables()[0] is s.sqrt_recip_alphas_cumprod and s._tables()[1] is s.sqrt_recipm1_alphas_cumprod
+    k10 = s._graph_key("x")
+    s._graphs["dummy"] = object()
+    s.make_schedule(10)
+    assert s._graph_key("x") == k10 and "dummy" in s._graphs           # same shape: tables updated in place
+    s.make_schedule(7)
+    assert s._graph_key("x") != k10 and not s._graphs                  # re-allocated: stale graphs dropped
+    with pytest.raises(ValueError):
+        SpacedSampler(val_diffusion().betas, "x0", False)
+
+
+def test_make_tiled_fn_matches_reference_semantics():
+    """terediff/utils/common.py:125-234: window list (edge-flush last window), gaussian weights (asymmetric midpoints),
+    weighted accumulation; an identity fn must be reproduced exactly up to round-off, tile bounds reach fn as kwargs."""
+    import numpy as np
+    import torch
+    from tair_b200 import legacy as L
+    assert L.sliding_windows(10, 12, 8, 4) == [(0, 8, 0, 8), (0, 8, 4, 12), (2, 10, 0, 8), (2, 10, 4, 12)]
+    assert L.sliding_windows(8, 8, 8, 4) == [(0, 8, 0, 8)]
+    w = L.gaussian_weights(4, 4)
+    var = 0.01
+    wx = [np.exp(-(x - 1.5) ** 2 / 16 / (2 * var)) / np.sqrt(2 * np.pi * var) for x in range(4)]
+    wy = [np.exp(-(y - 2.0) ** 2 / 16 / (2 * var)) / np.sqrt(2 * np.pi * var) for y in range(4)]
+    assert np.allclose(w, np.outer(wy, wx), rtol=1e-12)
+    x = torch.randn(2, 3, 20, 28, generator=torch.Generator().manual_seed(0))
+    seen = []
+
+    def fn(t, tag, hi, hi_end, wi, wi_end):
+        seen.append((hi, hi_end, wi, wi_end))
+        assert tag == "t" and t.shape[-2:] == (8, 8)
+        return t * 2
+    y = L.make_tiled_fn(fn, 8, 6)(x, "t")
+    assert torch.allclose(y, 2 * x, atol=1e-5) and seen == L.sliding_windows(20, 28, 8, 6)
+    up = L.make_tiled_fn(lambda t: torch.nn.functional.interpolate(t, scale_factor=2), 8, 8, scale=2, weight="uniform")(x[..., :16, :24])
+    assert up.shape == (2, 3, 32, 48)
+
+
+def test_reference_make_tiled_fn_agrees(tmp_path):
+    """Same inputs through the reference's make_tiled_fn when the tree is present (build container)."""
+    import pytest
+    import torch
+    from oracle import ref_harness as H
+    if not H.available():
+        pytest.skip("reference tree not present on this host")
+    H.install()
+    from terediff.utils.common import make_tiled_fn as ref_tiled
+    from tair_b200.legacy import make_tiled_fn
+    x = torch.randn(1, 4, 40, 56, generator=torch.Generator().manual_seed(1))
+    fn = lambda t: torch.tanh(t) * 3   # noqa: E731
+    for size, stride in ((16, 8), (16, 12), (32, 20)):
+        assert torch.equal(make_tiled_fn(fn, size, stride, progress=False)(x), ref_tiled(fn, size, stride, progress=False)(x))

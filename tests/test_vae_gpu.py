@@ -58,7 +58,8 @@ def test_decode_full_tile_psnr(vae):
         ref = OV.latent_to_image(sd, z)
     assert img.shape == (2, 3, 512, 512)
     p = OV.psnr(img, ref).min().item()
-    assert p > 35.0, p
+    print(f"VAE decode 512x512: PSNR {p:.1f} dB vs the fp32 oracle")
+    assert p >= 40.0, p   # the north star's final-image gate applied to the decoder alone
 
 
 def test_encode_vs_reference_fixture_and_oracle(vae, golden):
