@@ -131,8 +131,9 @@ def test_product_feedback_loop_decision_aligned_with_oracle(product, manifests):
         assert ((lg.max(-1)[0] - chosen)[cflips] <= ttol).all(), f"step {i}: a recognised character differs beyond the margin"
         # (f) polygons of the kept instances (pixel units, before the int32 cast) and their int32 form
         pp = tp["results"][0].polygons
-        assert pp.shape == to["polygons"].shape and (pp - to["polygons"]).abs().max(initial=0).item() < POLY_TOL_PX \
-            if pp.numel() else True
+        assert pp.shape == to["polygons"].shape
+        if pp.numel():
+            assert (pp - to["polygons"]).abs().max().item() < POLY_TOL_PX
         for a, b in zip(rp["pred_polys"], ro["pred_polys"]):
             assert a.dtype == np.int32 and a.shape == (16, 2) and np.abs(a - b).max() <= int(POLY_TOL_PX) + 1
         # (g) host side: strings and prompt from the same characters are identical; so is the re-encoded context
