@@ -81,10 +81,20 @@ typedef struct tair_epilogue {
                               a fixed-order reduction + epilogue kernel.  The split depends on the layer geometry
                               only, never on the batch, so results stay batch-independent.                     */
   int64_t workspace_bytes;
+  /* LayerNorm folded into the GEMM that consumes it (attention.py:252-254,264-272: norm1 -> attn1 q|k|v, norm2 -> attn2
+     to_q, norm3 -> GEGLU): A holds the RAW rows x, W holds W * gamma, and with ln_row_stats != NULL the accumulator is
+     rescaled per row BEFORE bias / activation:   acc' = rstd[m] * (acc - mean[m] * ln_col_sum[n])
+     ln_row_stats: fp32 [M, 2] = (mean, rstd) from tair_row_stats; ln_col_sum: fp32 [N] = sum_k W'[n, k] (of the bf16 values);
+     the caller folds beta into the bias: bias'[n] = bias[n] + sum_k beta[k] W[n, k].  GEMM only (not conv / split-K). */
+  const float* ln_row_stats;
+  const float* ln_col_sum;
 } tair_epilogue;
 
 /* out = epilogue(A[M,K] * W[N,K]^T).  A, W bf16, K contiguous; lda/ldw in elements
- * (multiples of 8).  fp32 accumulation in tensor memory (tcgen05). */
+ * (multiples of 8).  fp32 accumulation in tensor memory (tcgen05).
+ * Tile autotuning: the first un-captured call for a new problem shape times every legal N tile on the caller's stream and
+ * synchronises that stream ONCE (results are bit-identical for every candidate); later calls, and calls made while the
+ * stream is being captured, enqueue without synchronising.  TAIR_AUTOTUNE=0 disables tuning (closed-form tile pick). */
 int tair_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N,
                    int32_t K, const tair_epilogue* epi, void* stream);
 
@@ -112,6 +122,10 @@ int tair_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, 
 int64_t tair_groupnorm_workspace_bytes(int32_t B, int32_t groups);
 int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, const float* beta, int32_t B, int32_t HW,
                         int32_t C, int32_t groups, float eps, int32_t act, void* workspace, void* stream);
+
+/* Per-row LayerNorm statistics: out[m] = (mean, 1/sqrt(var + eps)) of x[m, :C]; bf16 rows, fp32 [M,2] out.  Feeds
+ * tair_epilogue.ln_row_stats of the GEMM that consumes the LayerNorm (the normalised tensor is never materialised). */
+int tair_row_stats(const void* x, int64_t ldx, float* out, int32_t M, int32_t C, float eps, void* stream);
 
 /* Row LayerNorm: y[m,:] = (x[m,:]-mean)/sqrt(var+eps)*gamma+beta; bf16 in/out, fp32 statistics. */
 int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
@@ -208,6 +222,15 @@ int tair_msda_fused(const void* value, const int64_t* spatial_shapes, const int6
 int tair_attention_seq_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int32_t H,
                             int32_t L, int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride,
                             int64_t tok_stride, float scale, void* stream);
+
+/* Detection post-processing of the TESTR head (transformer_detector.py:123-152 + spaced_sampler.py:298-306) for n_items =
+ * tiles x queries: scores[i] = sigmoid(mean_p pred_logits[i,p]) (one class), polygons[i, 2p+{0,1}] = ctrl point p in pixels
+ * (x * image_w, y * image_h), recs[i,c] = arg-max character of position c (uint8).  pred_logits fp32 [n_items, n_pts],
+ * pred_ctrl_points fp32 [n_items, n_pts, 2], pred_texts fp32 [n_items, n_chars, voc].  The score threshold is applied by
+ * the caller after ONE device->host copy of the three compact outputs. */
+int tair_testr_postprocess(const float* pred_logits, const float* pred_ctrl_points, const float* pred_texts,
+                           float* scores, float* polygons, uint8_t* recs, int32_t n_items, int32_t n_pts,
+                           int32_t n_chars, int32_t voc, float image_w, float image_h, void* stream);
 
 /* y[r,:] = softmax(scale * x[r,:]) over bf16 rows (cols % 8 == 0, <= 8192); bf16 [R,C] -> [C,R] batched transpose.
  * Used by the single-head 512-wide VAE attention (terediff/model/vae.py:253-281), evaluated as GEMM-softmax-GEMM. */

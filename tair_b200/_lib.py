@@ -38,6 +38,8 @@ class Epilogue(C.Structure):
         ("reserved", C.c_int32),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
+        ("ln_row_stats", C.c_void_p),
+        ("ln_col_sum", C.c_void_p),
     ]
 
 
@@ -56,6 +58,7 @@ SIGNATURES = {
     "tair_attention_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "tair_groupnorm_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "tair_groupnorm_nhwc": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp]),
+    "tair_row_stats": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _f32, _vp]),
     "tair_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _f32, _vp]),
     "tair_sampler_update": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "tair_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
@@ -73,6 +76,7 @@ SIGNATURES = {
     "tair_blend_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_msda_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tair_attention_seq_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _i32, _i64, _i64, _i64, _f32, _vp]),
+    "tair_testr_postprocess": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
     "tair_softmax_rows_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp]),
     "tair_transpose_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
 }

@@ -2,6 +2,7 @@
 // queries and TMA descriptor construction through the driver entry point.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <cudaTypedefs.h>
 
@@ -28,6 +29,15 @@ int check_launch(const char* what) {
     return TAIR_ERR_CUDA;
   }
   return TAIR_OK;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TAIR_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on == 1;
 }
 
 int num_sms() {

@@ -109,6 +109,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_grid_sync();   // barrier / tensor-memory set-up above overlaps the previous kernel's tail
   const uint32_t tm_S = tmem;
   const uint32_t tm_P = tmem + 128;
   const uint32_t tm_O = tmem + 192;
@@ -346,9 +347,252 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Key/value-stationary variant for SHORT contexts (the UNet / ControlNet cross-attention: Lk = 77 CLIP tokens,
+// attention.py:189-216 with context).  With one key block per query tile the flash kernel above degenerates into
+// 2560 CTAs that each pay barrier set-up, tensor-memory allocation and three dependent TMA round trips for ~1 us of
+// math (67 us per launch at 4096 x 77 against a 13 us HBM floor).  Here a CTA keeps K and V of one (batch, head) resident
+// and STREAMS query tiles through a 3-deep ring:
+//   warp 0      TMA: K, V once; Q tiles into the ring
+//   warp 1      MMA: S(i) = Q(i) K^T (M128 N80 K64) and O(i) = P(i) V (TS form, K = 80 keys)
+//   warps 2..5  softmax of tile i+1, THEN the drain of O(i): P is double buffered so that P(i+1) is written while
+//               P(i) V is still running, and the tensor pipe computes O(i+1) under the softmax of tile i+2
+// TMEM (256 columns): S fp32 [0,80) | P bf16x2 [80,120) and [120,160) | O fp32 [160,224).  A single key block needs no
+// online rescaling: P = exp2(S c - max c), O / sum(P).
+constexpr int KS_NK = 80;          // key columns per MMA (77 valid, zero rows from TMA's out-of-bounds fill)
+constexpr int KS_QSTAGES = 3;
+constexpr uint32_t KS_SM_K = 0;
+constexpr uint32_t KS_SM_V = KS_SM_K + TILE_BYTES;
+constexpr uint32_t KS_SM_Q = KS_SM_V + TILE_BYTES;
+constexpr uint32_t KS_SM_STG = KS_SM_Q + KS_QSTAGES * TILE_BYTES;   // 4 warps x (32 rows x 128 B) output staging
+constexpr uint32_t KS_SM_BAR = KS_SM_STG + 4 * 4096;
+constexpr uint32_t KS_SMEM = KS_SM_BAR + 160;
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_kvs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
+                int tiles_per_cta, int chunks) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + KS_SM_BAR;
+  const uint32_t kv_full = bar + 0, s_full = bar + 8, s_free = bar + 16, o_full = bar + 24, o_free = bar + 32;
+  auto p_full = [&](int b) { return bar + 40 + 8u * b; };
+  auto q_full = [&](int s) { return bar + 56 + 8u * s; };
+  auto q_empty = [&](int s) { return bar + 80 + 8u * s; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + KS_SM_BAR + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % chunks;
+  const int bh = blockIdx.x / chunks;
+  const int h = bh % p.H, seq = bh / p.H;
+  const int t0 = chunk * tiles_per_cta;
+  int nt = p.q_tiles - t0;
+  nt = nt < tiles_per_cta ? nt : tiles_per_cta;   // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    if ((sbase & 1023u) != 0) __trap();
+    mbar_init(kv_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    mbar_init(p_full(0), 4);
+    mbar_init(p_full(1), 4);
+    for (int s = 0; s < KS_QSTAGES; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_grid_sync();
+  const uint32_t tm_S = tmem, tm_P = tmem + 80, tm_O = tmem + 160;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_4d(sbase + KS_SM_K, &tmK, kv_full, h * AT_D, 0, 0, seq);
+      tma_load_4d(sbase + KS_SM_V, &tmV, kv_full, h * AT_D, 0, 0, seq);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {
+      const int qs = i % KS_QSTAGES;
+      mbar_wait(q_empty(qs), ((i / KS_QSTAGES) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(q_full(qs), TILE_BYTES);
+        tma_load_4d(sbase + KS_SM_Q + qs * TILE_BYTES, &tmQ, q_full(qs), h * AT_D, (t0 + i) * AT_BM, 0, seq);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, KS_NK, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    constexpr uint32_t desc_hi = umma_desc_hi_sw128(1024);
+    const uint32_t k_lo = umma_desc_lo(sbase + KS_SM_K, 16);
+    const uint32_t v_lo = umma_desc_lo(sbase + KS_SM_V, 16);
+    auto issue_s = [&](int i) {
+      const int qs = i % KS_QSTAGES;
+      mbar_wait(q_full(qs), (i / KS_QSTAGES) & 1);
+      tc_fence_after();
+      const uint32_t q_lo = umma_desc_lo(sbase + KS_SM_Q + qs * TILE_BYTES, 16);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k) umma_ss_lohi(tm_S, q_lo + 2 * k, k_lo + 2 * k, desc_hi, idesc_s, k != 0);
+        umma_commit(s_full);
+        umma_commit(q_empty(qs));
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_s(0);
+    for (int i = 0; i < nt; ++i) {
+      if (i + 1 < nt) {
+        mbar_wait(s_free, i & 1);     // S(i) is in the softmax threads' registers
+        tc_fence_after();
+        issue_s(i + 1);
+      }
+      mbar_wait(p_full(i & 1), (i >> 1) & 1);
+      if (i > 0) mbar_wait(o_free, (i - 1) & 1);   // O(i-1) has been drained
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < KS_NK / 16; ++k)
+          umma_ts_lohi(tm_O, tm_P + (i & 1) * 40 + k * 8, v_lo + k * (2048 >> 4), desc_hi, idesc_o, k != 0);
+        umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const float c = p.scale_log2;
+    const int kvalid = p.Lk;            // <= KS_NK
+    float inv_l[2] = {0.f, 0.f};        // 1 / row sum of tiles i (slot i & 1)
+
+    // O(i) / l(i) -> bf16 -> 128B-swizzled staging rows -> ONE bulk tensor store per warp (32 rows x 64 columns; rows past
+    // Lq are clipped by the hardware).  Thread-per-row 16-byte global stores touch 32 different lines per instruction: with
+    // a drain per tile they kept the LSU busier than the exponentials keep the MUFU.
+    uint8_t* stg = smem + KS_SM_STG + quad * 4096;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int sw7 = lane & 7;
+    auto drain = [&](int i) {
+      mbar_wait(o_full, i & 1);
+      tc_fence_after();
+      const float inv = inv_l[i & 1];
+      uint32_t ov[2][32];
+      tmem_ld_32x32(tm_O + lane_off, ov[0]);
+      tmem_ld_32x32(tm_O + lane_off + 32, ov[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);   // O is in registers: the next P V may overwrite the accumulator
+      if (elect_one()) tma_store_wait_read<0>();   // the previous store of this warp has left the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(ov[half][j + 0]) * inv, __uint_as_float(ov[half][j + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(ov[half][j + 2]) * inv, __uint_as_float(ov[half][j + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(ov[half][j + 4]) * inv, __uint_as_float(ov[half][j + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(ov[half][j + 6]) * inv, __uint_as_float(ov[half][j + 7]) * inv);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((((half * 32 + j) >> 3) ^ sw7) << 4)) = w;
+        }
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(&tmO),
+                     "r"(stg_u32), "r"(h * AT_D), "r"((t0 + i) * AT_BM + quad * 32), "r"(0), "r"(seq)
+                     : "memory");
+        tma_store_commit();
+      }
+    };
+
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint32_t sv[KS_NK];
+      {
+        uint32_t (&c0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
+        uint32_t (&c1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
+        uint32_t (&c2)[16] = *reinterpret_cast<uint32_t (*)[16]>(&sv[64]);
+        tmem_ld_32x32(tm_S + lane_off, c0);
+        tmem_ld_32x32(tm_S + lane_off + 32, c1);
+        tmem_ld_32x16(tm_S + lane_off + 64, c2);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < KS_NK; j += 4) {
+        if (j + 0 < kvalid) m0 = fmaxf(m0, __uint_as_float(sv[j + 0]));
+        if (j + 1 < kvalid) m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+        if (j + 2 < kvalid) m2 = fmaxf(m2, __uint_as_float(sv[j + 2]));
+        if (j + 3 < kvalid) m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+      }
+      const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
+      // P buffer (i & 1) was last read by P V(i-2), whose completion the drain of O(i-2) has already waited for
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      const uint32_t pdst = tm_P + lane_off + (i & 1) * 40;
+#pragma unroll
+      for (int cc = 0; cc < KS_NK; cc += 16) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + j + 0]), c, -mc));
+          float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + j + 1]), c, -mc));
+          float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + j + 2]), c, -mc));
+          float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + j + 3]), c, -mc));
+          if (cc + j + 0 >= kvalid) e0 = 0.f;
+          if (cc + j + 1 >= kvalid) e1 = 0.f;
+          if (cc + j + 2 >= kvalid) e2 = 0.f;
+          if (cc + j + 3 >= kvalid) e3 = 0.f;
+          l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+          pk[(j >> 1) + 0] = pack_bf16(e0, e1);
+          pk[(j >> 1) + 1] = pack_bf16(e2, e3);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(pdst + (cc >> 1)),
+                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                     : "memory");
+      }
+      inv_l[i & 1] = 1.f / ((l0 + l1) + (l2 + l3));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(i & 1));
+      if (i > 0) drain(i - 1);
+    }
+    drain(nt - 1);
+    if (elect_one()) tma_store_wait_all<0>();   // bulk stores must have completed before the CTA releases its smem
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, AT_TMEM_COLS);
+  }
+}
+
 // 4-D view (column, token, inner sequence index, outer sequence index) of a row-major [rows, ld] bf16 matrix
 int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int64_t n_inner, int64_t n_outer,
-             int64_t tok_stride, int64_t inner_stride, int64_t outer_stride) {
+             int64_t tok_stride, int64_t inner_stride, int64_t outer_stride, uint32_t box_rows = 128) {
   const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)L, (uint64_t)n_inner, (uint64_t)n_outer};
   // a size-1 dimension never advances; give it any legal (multiple of 16 B, non-zero) stride
   const uint64_t row = (uint64_t)ld * 2;
@@ -356,7 +600,7 @@ int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int6
   const uint64_t s2 = n_inner > 1 ? (uint64_t)inner_stride * row : s1 * (uint64_t)L;
   const uint64_t s3 = n_outer > 1 ? (uint64_t)outer_stride * row : (s2 > s1 ? s2 : s1) * 2;
   const uint64_t str[3] = {s1, s2, s3};
-  const uint32_t box[4] = {AT_D, 128, 1, 1};
+  const uint32_t box[4] = {AT_D, box_rows, 1, 1};
   return make_tmap_bf16(m, base, 4, dims, str, box, nullptr, 3);
 }
 
@@ -381,10 +625,37 @@ int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   if ((rc = make_map(&tmQ, q, ldq, H * 64, Lq, n_inner, n_outer, q_tok, q_inner, q_outer))) return rc;
   if ((rc = make_map(&tmK, k, ldk, H * 64, Lk, n_inner, n_outer, kv_tok, kv_inner, kv_outer))) return rc;
   if ((rc = make_map(&tmV, v, ldv, H * 64, Lk, n_inner, n_outer, kv_tok, kv_inner, kv_outer))) return rc;
+  static int kvs_mode = -1;   // TAIR_ATTN_KVS=0 disables the key/value-stationary kernel (A/B probe)
+  if (kvs_mode < 0) { const char* e = getenv("TAIR_ATTN_KVS"); kvs_mode = (e && atoi(e) == 0) ? 0 : 1; }
+  if (kvs_mode && group == 0 && !causal && n_inner == 1 && Lk <= KS_NK && bias == nullptr) {
+    // short context: stream the query tiles of a (batch, head) past resident K / V.  Chunks of query tiles per CTA so
+    // that roughly two CTAs per SM are in flight.
+    const long pairs = (long)n_outer * H;
+    // query tiles per CTA: minimise waves x (tiles per CTA + ~1.5 tiles of set-up) with two CTAs resident per SM
+    const long slots = 2L * num_sms();
+    int chunks = 1;
+    double best = 1e30;
+    for (int c = 1; c <= p.q_tiles; ++c) {
+      const int tpc = (p.q_tiles + c - 1) / c;
+      const int cc = (p.q_tiles + tpc - 1) / tpc;
+      const double cost = (double)((pairs * cc + slots - 1) / slots) * (tpc + 1.5);
+      if (cost < best - 1e-9) { best = cost; chunks = cc; }
+    }
+    const int tiles_per_cta = (p.q_tiles + chunks - 1) / chunks;
+    CUtensorMap tmO;
+    if ((rc = make_map(&tmO, o, ldo, H * 64, Lq, n_inner, n_outer, q_tok, q_inner, q_outer, 32))) return rc;
+    TAIR_SMEM_OPTIN(attn_kvs_kernel, KS_SMEM);
+    const long gridk = pairs * chunks;
+    TAIR_REQUIRE(gridk < (1l << 31), "attention: grid too large");
+    TAIR_LAUNCH((attn_kvs_kernel), (unsigned)gridk, AT_THREADS, KS_SMEM, static_cast<cudaStream_t>(stream), tmQ, tmK, tmV, tmO,
+                p, tiles_per_cta, chunks);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("attn_kvs_kernel");
+  }
   TAIR_SMEM_OPTIN(attn_tc_kernel, AT_SMEM);
   const long grid = (long)n_outer * n_inner * H * p.q_tiles;
   TAIR_REQUIRE(grid < (1l << 31), "attention: grid too large");
-  attn_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  TAIR_LAUNCH((attn_tc_kernel), (unsigned)grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream), tmQ, tmK, tmV, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("attn_tc_kernel");
 }

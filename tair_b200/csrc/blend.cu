@@ -29,6 +29,7 @@ __device__ __forceinline__ float ramp(int l, int T, int fade) {
 }
 
 __global__ void blend_tiles_kernel(const BlendParams p) {
+  pdl_grid_sync();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= p.out_w) return;
@@ -77,7 +78,7 @@ extern "C" int tair_blend_tiles(const float* tiles, float* out, int32_t n_tiles,
   BlendParams p{tiles, out, n_tiles, n_h, n_w, C, tile, stride, overlap > 0 ? overlap : 1, out_h, out_w};
   if (overlap == 0) p.fade = 0;
   dim3 block(256), grid((out_w + 255) / 256, out_h);
-  blend_tiles_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  TAIR_LAUNCH((blend_tiles_kernel), grid, block, 0, static_cast<cudaStream_t>(stream), p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("blend_tiles_kernel");
 }

@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/tair_b200.h"
 
 namespace tair {
@@ -53,6 +55,36 @@ int num_sms();
     }                                                                                                       \
   } while (0)
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and begins — after its launch-independent set-up (barrier
+// initialisation, tensor-memory allocation, descriptor prefetch) — with pdl_grid_sync(): `griddepcontrol.wait` blocks until
+// the preceding kernel of the stream has completed and flushed its memory, and `griddepcontrol.launch_dependents` lets the
+// NEXT kernel's CTAs be scheduled as soon as SMs free up.  A denoising step is ~620-920 short kernels; this overlaps each
+// kernel's launch latency and prologue with its predecessor's tail.  No kernel touches global memory before the wait, so
+// the stream's serial semantics are preserved exactly.  TAIR_PDL=0 turns the attribute off (plain serialisation).
+// ---------------------------------------------------------------------------
+bool pdl_enabled();
+
+template <typename... KP, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+// TAIR_LAUNCH((kernel<T, U>), grid, block, smem, stream, args...): the parentheses keep template commas out of the macro
+#define TAIR_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)::tair::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+
 // TMA descriptor construction through the driver entry point (no -lcuda).
 // dims/strides follow cuTensorMapEncodeTiled: dim[0] is the contiguous one,
 // strides are BYTES for dims 1..rank-1.
@@ -64,6 +96,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // device PTX wrappers
 // ---------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// see the PDL note above: wait for the preceding kernel (completion + memory flush), then let the next one be scheduled
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -386,9 +424,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }  // MUFU.RCP, no IEEE divide
-// exact (erf) GELU, matching torch.nn.functional.gelu default
+// exact (erf) GELU, matching torch.nn.functional.gelu default.  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. at
+// fp32 round-off): 15 instructions with two MUFU ops (RCP, EX2) against ~30 branchy ones for erff() — the GEGLU epilogue
+// of the transformer feed-forward GEMMs was bound by it (ncu: XU pipe 15 %, tensor pipe 35 %, profiles/round1_summary.md).
+//   gelu(x) = x/2 (1 + erf(x/sqrt 2)) = x/2 + |x|/2 * erf(|x|/sqrt 2),  erf(z) = 1 - t(a1 + t(a2 + t(a3 + t(a4 + t a5)))) e^{-z^2}
 __device__ __forceinline__ float gelu_f(float x) {
-  return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = ex2_approx(x * x * -0.72134752044448170f);   // exp(-z^2) = 2^(-x^2 log2(e) / 2)
+  const float erf_abs = fmaf(-p * t, e, 1.f);
+  return fmaf(0.5f * fabsf(x), erf_abs, 0.5f * x);
+}
+
+// GELU in its tanh form through the hardware tanh (one MUFU op, 6 instructions): |gelu_tanh - gelu_erf| <= 4.8e-4 over the
+// whole range and <= 2e-4 for |x| <= 2 — 8x below the bf16 rounding (3.9e-3 at 1.0) of the value it produces.  Used ONLY by
+// the GEGLU epilogue of the transformer feed-forward GEMMs (attention.py:19-27), whose epilogue is issue-bound: two
+// accumulators, two biases, the gate activation and a product per output element inside a K = 320..1280 mainloop.
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float u = x * fmaf(x * x, 0.0356774081363001f, 0.7978845608028654f);
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return fmaf(h, t, h);
 }
 
 #endif  // __CUDACC__

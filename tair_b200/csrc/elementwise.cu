@@ -24,6 +24,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ coef2, const float* __restrict__ post_var,
                                       float cfg_scale, const float* __restrict__ cfg_scale_dev, int per_sample,
                                       int total) {
+  pdl_grid_sync();
   // 4 elements per thread; per_sample % 4 == 0 so a float4 never straddles two samples
   const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= total) return;
@@ -58,6 +59,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
 
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B,
                                           int dim, float max_period) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= B * dim) return;
@@ -75,6 +77,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, __nv_bf
 // (B, C, HW) fp32 -> [B, HW, Cpad] bf16 (channels >= C zero-filled); 32x32 smem transpose
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int HW,
                                     int Cpad) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -93,6 +96,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16*
 // [B, HW, ld] bf16 (first C channels) -> (B, C, HW) fp32
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int HW,
                                     int64_t ld) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -121,6 +125,7 @@ __device__ __forceinline__ uint4 add_bf16x8(uint4 a, uint4 b) {
 // out[M, C1+C2] = [a[M,C1] | b[M,C2] (+ c[M,C2])]; one 16-byte vector per thread
 __global__ void concat_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                   const uint4* __restrict__ c, uint4* __restrict__ out, int64_t M, int v1, int v2) {
+  pdl_grid_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int vt = v1 + v2;
   if (i >= M * vt) return;
@@ -139,12 +144,14 @@ __global__ void concat_add_kernel(const uint4* __restrict__ a, const uint4* __re
 
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                            int64_t n) {
+  pdl_grid_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = add_bf16x8(__ldg(a + i), __ldg(b + i));
 }
 
 // [B, H, W, C] -> [B, 2H, 2W, C] nearest; one 16-byte vector of the OUTPUT per thread
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vc) {
+  pdl_grid_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)B * 4 * H * W * vc;
   if (i >= total) return;
@@ -162,6 +169,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 template <int MAXV>
 __global__ void softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
                                     int64_t ldy, int rows, int cols, float scale_log2) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -208,6 +216,7 @@ __global__ void softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t
 // bf16 [R, C] (row stride ldi) -> [C, R] (row stride ldo), batched over blockIdx.z; 32x32 smem tiles
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ldi, int64_t in_batch,
                                       __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t out_batch, int R, int C) {
+  pdl_grid_sync();
   __shared__ __nv_bfloat16 tile[32][34];
   in += (int64_t)blockIdx.z * in_batch;
   out += (int64_t)blockIdx.z * out_batch;
@@ -245,7 +254,7 @@ extern "C" int tair_sampler_update(const float* x, const float* v_cond, const fl
                    (!pred_x0 || al16(pred_x0)), "sampler_update: tensors must be 16-byte aligned");
   const int total = B * per_sample;
   const int threads = 256, grid = (total / 4 + threads - 1) / threads;
-  sampler_update_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((sampler_update_kernel), grid, threads, 0, static_cast<cudaStream_t>(stream), 
       x, v_cond, v_uncond, noise, x_prev, pred_x0, t, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod,
       posterior_mean_coef1, posterior_mean_coef2, posterior_variance, cfg_scale, cfg_scale_dev, per_sample, total);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -256,7 +265,7 @@ extern "C" int tair_timestep_embedding(const int64_t* t, void* out, int32_t B, i
                                        void* stream) {
   TAIR_REQUIRE(t && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
   const int n = B * dim;
-  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((timestep_embedding_kernel), (n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), 
       t, reinterpret_cast<__nv_bfloat16*>(out), B, dim, max_period);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("timestep_embedding_kernel");
@@ -266,7 +275,7 @@ extern "C" int tair_nchw_to_nhwc_bf16(const float* in, void* out, int32_t B, int
                                       void* stream) {
   TAIR_REQUIRE(in && out && B > 0 && C > 0 && HW > 0 && Cpad >= C, "nchw_to_nhwc: bad arguments");
   dim3 grid((HW + 31) / 32, (Cpad + 31) / 32, B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((nchw_to_nhwc_kernel), grid, block, 0, static_cast<cudaStream_t>(stream), 
       in, reinterpret_cast<__nv_bfloat16*>(out), C, HW, Cpad);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("nchw_to_nhwc_kernel");
@@ -276,7 +285,7 @@ extern "C" int tair_nhwc_to_nchw_f32(const void* in, int64_t ld, float* out, int
                                      void* stream) {
   TAIR_REQUIRE(in && out && B > 0 && C > 0 && HW > 0 && ld >= C, "nhwc_to_nchw: bad arguments");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((nhwc_to_nchw_kernel), grid, block, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(in), out, C, HW, ld);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("nhwc_to_nchw_kernel");
@@ -288,7 +297,7 @@ extern "C" int tair_concat_add(const void* a, const void* b, const void* c, void
   TAIR_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "concat_add: channel counts must be multiples of 8");
   TAIR_REQUIRE(al16(a) && al16(b) && al16(out) && (!c || al16(c)), "concat_add: tensors must be 16-byte aligned");
   const int64_t n = M * ((C1 + C2) / 8);
-  concat_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((concat_add_kernel), (unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<const uint4*>(c),
       reinterpret_cast<uint4*>(out), M, C1 / 8, C2 / 8);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -299,7 +308,7 @@ extern "C" int tair_add_bf16(const void* a, const void* b, void* out, int64_t n,
   TAIR_REQUIRE(a && b && out && n > 0 && n % 8 == 0, "add: n must be a positive multiple of 8");
   TAIR_REQUIRE(al16(a) && al16(b) && al16(out), "add: tensors must be 16-byte aligned");
   const int64_t nv = n / 8;
-  add_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((add_kernel), (unsigned)((nv + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), nv);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("add_kernel");
@@ -310,7 +319,7 @@ extern "C" int tair_upsample2x_nhwc(const void* in, void* out, int32_t B, int32_
   TAIR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x: bad arguments");
   TAIR_REQUIRE(al16(in) && al16(out), "upsample2x: tensors must be 16-byte aligned");
   const int64_t n = (int64_t)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((upsample2x_kernel), (unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), B, H, W, C / 8);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("upsample2x_kernel");
@@ -328,10 +337,10 @@ extern "C" int tair_softmax_rows_bf16(const void* x, int64_t ldx, void* y, int64
   const float sl2 = scale * 1.4426950408889634f;
   const int warps = 4, grid = (rows + warps - 1) / warps;
   const int nvec = cols / 8;
-  if (nvec <= 32) softmax_rows_kernel<1><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
-  else if (nvec <= 128) softmax_rows_kernel<4><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
-  else if (nvec <= 512) softmax_rows_kernel<16><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
-  else softmax_rows_kernel<32><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, rows, cols, sl2);
+  if (nvec <= 32) TAIR_LAUNCH((softmax_rows_kernel<1>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, rows, cols, sl2);
+  else if (nvec <= 128) TAIR_LAUNCH((softmax_rows_kernel<4>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, rows, cols, sl2);
+  else if (nvec <= 512) TAIR_LAUNCH((softmax_rows_kernel<16>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, rows, cols, sl2);
+  else TAIR_LAUNCH((softmax_rows_kernel<32>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, rows, cols, sl2);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("softmax_rows_kernel");
 }
@@ -340,7 +349,7 @@ extern "C" int tair_transpose_bf16(const void* in, int64_t ldi, int64_t in_batch
                                    int64_t out_batch_stride, int32_t batch, int32_t R, int32_t C, void* stream) {
   TAIR_REQUIRE(in && out && batch > 0 && R > 0 && C > 0 && ldi >= C && ldo >= R, "transpose: bad arguments");
   dim3 grid((C + 31) / 32, (R + 31) / 32, batch), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((transpose_bf16_kernel), grid, block, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(in), ldi, in_batch_stride, reinterpret_cast<__nv_bfloat16*>(out), ldo,
       out_batch_stride, R, C);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -353,6 +362,7 @@ namespace tair {
 namespace {
 __global__ void gather_rows_kernel(const uint4* __restrict__ x, int64_t ldx16, const int32_t* __restrict__ idx,
                                    uint4* __restrict__ y, int64_t ldy16, int64_t rows, int vec_per_row) {
+  pdl_grid_sync();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rows * vec_per_row) return;
   const int64_t r = t / vec_per_row;
@@ -361,6 +371,7 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ x, int64_t ldx16, c
 }
 
 __global__ void leaky_relu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t n16, float slope) {
+  pdl_grid_sync();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n16) return;
   const uint4 q = __ldg(x + t);
@@ -387,7 +398,7 @@ extern "C" int tair_gather_rows_bf16(const void* x, int64_t ldx, const int32_t* 
                "gather_rows: tensors must be 16-byte aligned");
   const int vpr = cols / 8;
   const int64_t total = rows * vpr;
-  tair::gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((tair::gather_rows_kernel), (unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), ldx / 8, idx, reinterpret_cast<uint4*>(y), ldy / 8, rows, vpr);
   tair::g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return tair::check_launch("gather_rows_kernel");
@@ -398,7 +409,7 @@ extern "C" int tair_leaky_relu_bf16(const void* x, void* y, int64_t n, float slo
   TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(y) % 16) == 0,
                "leaky_relu: tensors must be 16-byte aligned");
   const int64_t n16 = n / 8;
-  tair::leaky_relu_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((tair::leaky_relu_kernel), (unsigned)((n16 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n16, slope);
   tair::g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return tair::check_launch("leaky_relu_kernel");

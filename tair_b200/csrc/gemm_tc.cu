@@ -136,6 +136,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
       const float* rg = nullptr;
       if (e.rowgroup != nullptr && row_ok)
         rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
+      // folded LayerNorm: acc' = rstd * (acc - mean * colsum[n]) = acc * ln_r + ln_c * colsum[n]
+      float ln_r = 1.f, ln_c = 0.f;
+      const float* lcs = e.ln_row_stats != nullptr ? e.ln_col_sum : nullptr;
+      if (lcs != nullptr && row_ok) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(e.ln_row_stats) + m);
+        ln_r = st.y;
+        ln_c = -st.x * st.y;
+      }
 
       if constexpr (ACT == TAIR_ACT_GEGLU) {
         constexpr int HALF = BN / 2;
@@ -154,11 +162,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
             for (int j = 0; j < 16; ++j) {
               float a = __uint_as_float(rv[j]);
               float g = __uint_as_float(rgt[j]);
+              if (lcs != nullptr) {
+                a = fmaf(a, ln_r, ln_c * __ldg(lcs + nv + j));
+                g = fmaf(g, ln_r, ln_c * __ldg(lcs + ng + j));
+              }
               if (e.bias != nullptr) {
                 a += __ldg(e.bias + nv + j);
                 g += __ldg(e.bias + ng + j);
               }
-              v[j] = a * gelu_f(g);
+              v[j] = a * gelu_tanh_f(g);
             }
             epi_finish_store<16>(p, m, tn * HALF + c, nout_total, v);
           }
@@ -176,6 +188,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float a = __uint_as_float(r[j]);
+                if (lcs != nullptr) a = fmaf(a, ln_r, ln_c * __ldg(lcs + n + j));
                 if (e.bias != nullptr) a += __ldg(e.bias + n + j);
                 if (rg != nullptr) a += __ldg(rg + n + j);
                 v[j] = apply_act<ACT>(a);
@@ -185,6 +198,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
               for (int j = 0; j < 32; ++j) {
                 float a = __uint_as_float(r[j]);
                 if (n + j < p.N) {
+                  if (lcs != nullptr) a = fmaf(a, ln_r, ln_c * __ldg(lcs + n + j));
                   if (e.bias != nullptr) a += __ldg(e.bias + n + j);
                   if (rg != nullptr) a += __ldg(rg + n + j);
                 }
@@ -221,6 +235,14 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
   const __nv_bfloat16* resp = (e.residual != nullptr && row_ok)
                                   ? reinterpret_cast<const __nv_bfloat16*>(e.residual) + (int64_t)m * e.ldr : nullptr;
+  // folded LayerNorm (tair_epilogue.ln_row_stats): acc' = rstd * (acc - mean * colsum[n]) = acc * ln_r + ln_c * colsum[n]
+  float ln_r = 1.f, ln_c = 0.f;
+  const float* lcs = e.ln_row_stats != nullptr ? e.ln_col_sum : nullptr;
+  if (lcs != nullptr && row_ok) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(e.ln_row_stats) + m);
+    ln_r = st.y;
+    ln_c = -st.x * st.y;
+  }
   const uint32_t stg_u32 = smem_u32(stg);
   const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
 
@@ -277,8 +299,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a = __uint_as_float(rv[j]), gt = __uint_as_float(rgt[j]);
+            if (lcs != nullptr) {   // warp-uniform; the column sums are broadcast loads like the bias
+              a = fmaf(a, ln_r, ln_c * __ldg(lcs + nv + j));
+              gt = fmaf(gt, ln_r, ln_c * __ldg(lcs + ng + j));
+            }
             if (e.bias != nullptr) { a += __ldg(e.bias + nv + j); gt += __ldg(e.bias + ng + j); }
-            v[h2 * 16 + j] = a * gelu_f(gt);
+            v[h2 * 16 + j] = a * gelu_tanh_f(gt);
           }
         }
       } else {
@@ -286,6 +312,16 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         tmem_ld_32x32(taddr + c0 + g, r);
         tmem_ld_wait();
         if (n + 32 <= p.N) {
+          if (lcs != nullptr) {   // folded LayerNorm first: it rescales the raw accumulator
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(lcs + n) + q);
+              r[q * 4 + 0] = __float_as_uint(fmaf(__uint_as_float(r[q * 4 + 0]), ln_r, ln_c * t.x));
+              r[q * 4 + 1] = __float_as_uint(fmaf(__uint_as_float(r[q * 4 + 1]), ln_r, ln_c * t.y));
+              r[q * 4 + 2] = __float_as_uint(fmaf(__uint_as_float(r[q * 4 + 2]), ln_r, ln_c * t.z));
+              r[q * 4 + 3] = __float_as_uint(fmaf(__uint_as_float(r[q * 4 + 3]), ln_r, ln_c * t.w));
+            }
+          }
           if (rg != nullptr && p.vec_rg) {
             // per-row add rows (positional projections): every lane reads its own row, so use 16-byte loads
 #pragma unroll
@@ -325,6 +361,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
           for (int j = 0; j < 32; ++j) {
             float a = __uint_as_float(r[j]);
             if (n + j < p.N) {
+              if (lcs != nullptr) a = fmaf(a, ln_r, ln_c * __ldg(lcs + n + j));
               if (e.bias != nullptr) a += __ldg(e.bias + n + j);
               if (rg != nullptr) a += __ldg(rg + n + j);
             }
@@ -416,6 +453,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_grid_sync();   // set-up above overlaps the previous kernel's tail; no global memory is touched before this point
 
   const int num_tiles = p.tiles_m * p.tiles_n * p.splits;   // work items: (tile, K split)
   const int mn_tiles = p.tiles_m * p.tiles_n;
@@ -635,6 +673,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_grid_sync();
 
   const int tiles_m2 = (p.tiles_m + 1) >> 1;  // 256-row tiles
   const int num_tiles = tiles_m2 * p.tiles_n;
@@ -778,7 +817,7 @@ int launch_bn2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   const int tiles2 = ((p.tiles_m + 1) / 2) * p.tiles_n;
   int pairs = num_sms() / 2;
   if (tiles2 < pairs) pairs = tiles2;
-  gemm_tc2_kernel<BN><<<2 * pairs, GEMM_THREADS, Cfg2<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC64, tmC32, p);
+  TAIR_LAUNCH((gemm_tc2_kernel<BN>), 2 * pairs, GEMM_THREADS, Cfg2<BN>::SMEM_BYTES, st, tmA, tmB, tmC64, tmC32, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("gemm_tc2_kernel");
 }
@@ -789,7 +828,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   TAIR_SMEM_OPTIN(gemm_tc_kernel<BN>, Cfg<BN>::SMEM_BYTES);
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmC64, tmC32, p);
+  TAIR_LAUNCH((gemm_tc_kernel<BN>), grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmB, tmC64, tmC32, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("gemm_tc_kernel");
 }
@@ -891,6 +930,11 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   if (e->rowgroup) TAIR_REQUIRE(e->rows_per_group != 0, "rows_per_group must be non-zero");
   if (e->act == TAIR_ACT_GEGLU)
     TAIR_REQUIRE(e->rowgroup == nullptr, "GEGLU epilogue does not take a row-group add");
+  TAIR_REQUIRE((e->ln_row_stats == nullptr) == (e->ln_col_sum == nullptr), "ln_row_stats and ln_col_sum go together");
+  if (e->ln_row_stats)
+    TAIR_REQUIRE(p.conv == 0 && (reinterpret_cast<uintptr_t>(e->ln_row_stats) % 8) == 0 &&
+                     (reinterpret_cast<uintptr_t>(e->ln_col_sum) % 16) == 0 && p.N % 4 == 0,
+                 "folded LayerNorm: GEMM only, row stats 8-byte / column sums 16-byte aligned, N %% 4 == 0");
   p.epi = *e;
   {
     const char* d = getenv("TAIR_GEMM_DEBUG");
@@ -914,6 +958,7 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
 // applies the epilogue.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, const tair_epilogue e) {
+  pdl_grid_sync();
   const int64_t idx4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread = 4 consecutive columns
   const int n4 = N >> 2;
   if (idx4 >= (int64_t)M * n4) return;
@@ -968,7 +1013,7 @@ int dispatch_splitk(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmPara
   int rc = dispatch(tmA, W, ldw, q, bn, false, st);
   if (rc) return rc;
   const int64_t n4 = (int64_t)p.M * (p.N / 4);
-  splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws), splits, p.M, p.N, p.epi);
+  TAIR_LAUNCH((splitk_reduce_kernel), (unsigned)((n4 + 255) / 256), 256, 0, st, reinterpret_cast<const float*>(ws), splits, p.M, p.N, p.epi);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("splitk_reduce_kernel");
 }
@@ -1034,7 +1079,8 @@ int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const
   std::memset(&key, 0, sizeof(key));
   cudaGetDevice(&key.dev);
   key.conv = p.conv; key.M = p.M; key.N = p.N; key.K = p.K; key.Wo = p.Wo; key.stride = p.stride; key.act = act;
-  key.flags = (p.epi.out_fp32 ? 1 : 0) | (p.vec_out ? 2 : 0) | (p.epi.residual ? 4 : 0) | (p.epi.rowgroup ? 8 : 0);
+  key.flags = (p.epi.out_fp32 ? 1 : 0) | (p.vec_out ? 2 : 0) | (p.epi.residual ? 4 : 0) | (p.epi.rowgroup ? 8 : 0) |
+              (p.epi.ln_row_stats ? 16 : 0);
   {
     std::lock_guard<std::mutex> lk(g_tune_mu);
     auto it = g_tuned.find(key);

@@ -51,6 +51,7 @@ __device__ __forceinline__ void load_vec8<__nv_bfloat16>(const __nv_bfloat16* p,
 
 template <typename VT, typename OT>
 __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaParams p) {
+  pdl_grid_sync();
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long item = gtid / p.lanes_per_item;
   const int part = (int)(gtid - item * p.lanes_per_item);
@@ -131,6 +132,7 @@ constexpr int MSDA_MAX_LP = 32;
 
 template <int LT, int PT, typename PJ>  // compile-time (levels, points) or 0 for runtime loops; PJ = proj element type
 __global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p) {
+  pdl_grid_sync();
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long item = gtid / p.lanes_per_item;
   const int part = (int)(gtid - item * p.lanes_per_item);
@@ -233,6 +235,7 @@ template <> struct ProjVec<__nv_bfloat16> {
 // sampling coordinates, bilinear weights, addresses — is amortised over twice as many channels (2 lanes per item for D=32).
 template <typename PJ, int CPL>
 __global__ void __launch_bounds__(256, CPL == 8 ? 4 : 3) msda_fused44_kernel(const MsdaFusedParams p) {
+  pdl_grid_sync();
   constexpr int LP = 16, PER = ProjVec<PJ>::PER, NV = CPL / 8;
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long item = gtid / p.lanes_per_item;
@@ -358,10 +361,10 @@ extern "C" int tair_msda_forward(const void* value, const int64_t* spatial_shape
   const long grid = (threads_total + block - 1) / block;
   TAIR_REQUIRE(grid < (1l << 31), "msda_forward: problem too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (value_bf16 && out_bf16) msda_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)grid, block, 0, st>>>(p);
-  else if (value_bf16) msda_fwd_kernel<__nv_bfloat16, float><<<(unsigned)grid, block, 0, st>>>(p);
-  else if (out_bf16) msda_fwd_kernel<float, __nv_bfloat16><<<(unsigned)grid, block, 0, st>>>(p);
-  else msda_fwd_kernel<float, float><<<(unsigned)grid, block, 0, st>>>(p);
+  if (value_bf16 && out_bf16) TAIR_LAUNCH((msda_fwd_kernel<__nv_bfloat16, __nv_bfloat16>), (unsigned)grid, block, 0, st, p);
+  else if (value_bf16) TAIR_LAUNCH((msda_fwd_kernel<__nv_bfloat16, float>), (unsigned)grid, block, 0, st, p);
+  else if (out_bf16) TAIR_LAUNCH((msda_fwd_kernel<float, __nv_bfloat16>), (unsigned)grid, block, 0, st, p);
+  else TAIR_LAUNCH((msda_fwd_kernel<float, float>), (unsigned)grid, block, 0, st, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("msda_fwd_kernel");
 }
@@ -396,17 +399,17 @@ extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes,
   if (fast44 && D % 16 == 0 && !getenv("TAIR_MSDA_CPL8")) {
     p.lanes_per_item = D / 16;
     const long grid16 = (p.items * p.lanes_per_item + 255) / 256;
-    if (proj_bf16) msda_fused44_kernel<__nv_bfloat16, 16><<<(unsigned)grid16, 256, 0, st>>>(p);
-    else msda_fused44_kernel<float, 16><<<(unsigned)grid16, 256, 0, st>>>(p);
+    if (proj_bf16) TAIR_LAUNCH((msda_fused44_kernel<__nv_bfloat16, 16>), (unsigned)grid16, 256, 0, st, p);
+    else TAIR_LAUNCH((msda_fused44_kernel<float, 16>), (unsigned)grid16, 256, 0, st, p);
   } else if (fast44) {
-    if (proj_bf16) msda_fused44_kernel<__nv_bfloat16, 8><<<(unsigned)grid, 256, 0, st>>>(p);
-    else msda_fused44_kernel<float, 8><<<(unsigned)grid, 256, 0, st>>>(p);
+    if (proj_bf16) TAIR_LAUNCH((msda_fused44_kernel<__nv_bfloat16, 8>), (unsigned)grid, 256, 0, st, p);
+    else TAIR_LAUNCH((msda_fused44_kernel<float, 8>), (unsigned)grid, 256, 0, st, p);
   } else if (L == 4 && P == 4) {
-    if (proj_bf16) msda_fused_kernel<4, 4, __nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
-    else msda_fused_kernel<4, 4, float><<<(unsigned)grid, 256, 0, st>>>(p);
+    if (proj_bf16) TAIR_LAUNCH((msda_fused_kernel<4, 4, __nv_bfloat16>), (unsigned)grid, 256, 0, st, p);
+    else TAIR_LAUNCH((msda_fused_kernel<4, 4, float>), (unsigned)grid, 256, 0, st, p);
   } else {
-    if (proj_bf16) msda_fused_kernel<0, 0, __nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p);
-    else msda_fused_kernel<0, 0, float><<<(unsigned)grid, 256, 0, st>>>(p);
+    if (proj_bf16) TAIR_LAUNCH((msda_fused_kernel<0, 0, __nv_bfloat16>), (unsigned)grid, 256, 0, st, p);
+    else TAIR_LAUNCH((msda_fused_kernel<0, 0, float>), (unsigned)grid, 256, 0, st, p);
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("msda_fused_kernel");

@@ -46,8 +46,22 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
-// grid (slabs, B); block = vec_per_row * rows_per_iter threads (<= 320, so <= 2560 channel slots)
-__global__ void gn_stats_kernel(const GnParams p) {
+// SiLU through the hardware tanh: x * sigmoid(x) = h + h * tanh(h), h = x / 2 — ONE MUFU op (tanh.approx, max relative error
+// 2^-11, i.e. below the bf16 rounding of the result) instead of EX2 + RCP.  GroupNorm+SiLU writes 21 M elements per
+// launch at the 64x64 level: two MUFU ops per element kept the XU pipe busy for ~10 us of a ~13 us memory-bound kernel.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// grid (slabs, B); block = vec_per_row * rows_per_iter threads (<= 320, so <= 2560 channel slots).
+// U = 16-byte loads in flight per thread: the statistics pass is pure latency hiding (no stores), so every thread issues
+// its whole slab share up front whenever it fits.
+template <int U>
+__global__ void __launch_bounds__(320) gn_stats_kernel(const GnParams p) {
+  pdl_grid_sync();
   __shared__ float s_part[2][2560];  // per (row-phase, channel) partial sum / sum of squares
   const int b = blockIdx.y, slab = blockIdx.x;
   const int vec = threadIdx.x % p.vec_per_row;
@@ -61,15 +75,14 @@ __global__ void gn_stats_kernel(const GnParams p) {
   int r1 = r0 + p.rows_per_slab;
   if (r1 > p.HW) r1 = p.HW;
   const __nv_bfloat16* xb = p.x + (int64_t)b * p.HW * p.C + c0;
-  // 4 independent 16-byte loads in flight per thread (memory-level parallelism), then a scalar tail
   int r = r0 + rsub;
   const int step = p.rows_per_iter;
-  for (; r + 3 * step < r1; r += 4 * step) {
-    uint4 q[4];
+  for (; r + (U - 1) * step < r1; r += U * step) {
+    uint4 q[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)(r + u * step) * p.C));
+    for (int u = 0; u < U; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)(r + u * step) * p.C));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const float2 a = unpack_bf16(q[u].x), b2 = unpack_bf16(q[u].y), c = unpack_bf16(q[u].z), d = unpack_bf16(q[u].w);
       const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
 #pragma unroll
@@ -83,39 +96,37 @@ __global__ void gn_stats_kernel(const GnParams p) {
     for (int i = 0; i < 8; ++i) { sm[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
   }
   // deterministic block reduction (no atomics: results must not depend on scheduling, the sampler is a 50-step
-  // recurrence): slot = rsub * C + channel, then one thread per group sums its slots in a fixed order
+  // recurrence): slot = rsub * C + channel, then one thread per (group, statistic) sums its slots in a fixed order
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     s_part[0][rsub * p.C + c0 + i] = sm[i];
     s_part[1][rsub * p.C + c0 + i] = sq[i];
   }
   __syncthreads();
-  if (threadIdx.x < p.G) {
-    const int g = threadIdx.x;
-    float ps = 0.f, pq = 0.f;
+  if (threadIdx.x < 2 * p.G) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const float* sp = s_part[which];
+    float acc = 0.f;
     for (int rs = 0; rs < p.rows_per_iter; ++rs) {
       const int base = rs * p.C + g * p.cpg;
-      for (int c = 0; c < p.cpg; ++c) {
-        ps += s_part[0][base + c];
-        pq += s_part[1][base + c];
-      }
+      for (int c = 0; c < p.cpg; ++c) acc += sp[base + c];
     }
-    float* w = p.ws + ((int64_t)(b * p.slabs + slab) * p.G) * 2;
-    w[2 * g] = ps;
-    w[2 * g + 1] = pq;
+    p.ws[((int64_t)(b * p.slabs + slab) * p.G) * 2 + threadIdx.x] = acc;
   }
 }
 
-template <int ACT>
-__global__ void gn_apply_kernel(const GnParams p) {
+template <int ACT, int U>
+__global__ void __launch_bounds__(320) gn_apply_kernel(const GnParams p) {
+  pdl_grid_sync();
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y, slab = blockIdx.x;
   if (threadIdx.x < p.G) {
     float s = 0.f, q = 0.f;
     const float* w = p.ws + (int64_t)b * p.slabs * p.G * 2 + threadIdx.x * 2;
     for (int i = 0; i < p.slabs; ++i) {
-      s += w[(int64_t)i * p.G * 2];
-      q += w[(int64_t)i * p.G * 2 + 1];
+      const float2 t = *reinterpret_cast<const float2*>(w + (int64_t)i * p.G * 2);
+      s += t.x;
+      q += t.y;
     }
     const float n = (float)p.HW * (float)p.cpg;
     const float mean = s / n;
@@ -124,45 +135,130 @@ __global__ void gn_apply_kernel(const GnParams p) {
     s_mean[threadIdx.x] = mean;
     s_rstd[threadIdx.x] = rsqrtf(var + p.eps);
   }
-  __syncthreads();
   const int vec = threadIdx.x % p.vec_per_row;
   const int rsub = threadIdx.x / p.vec_per_row;
   const int c0 = vec * 8;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int g = (c0 + i) / p.cpg;
-    const float ga = __ldg(p.gamma + c0 + i) * s_rstd[g];
-    sc[i] = ga;
-    sh[i] = __ldg(p.beta + c0 + i) - s_mean[g] * ga;
-  }
   const int r0 = slab * p.rows_per_slab;
   int r1 = r0 + p.rows_per_slab;
   if (r1 > p.HW) r1 = p.HW;
   const int64_t base = (int64_t)b * p.HW * p.C + c0;
-  auto finish = [&](float (&f)[8], int r) {
+  const int step = p.rows_per_iter;
+  int r = r0 + rsub;
+  // the first batch of loads is issued BEFORE the statistics are folded: it does not depend on them
+  uint4 q0[U];
+  const bool first = r + (U - 1) * step < r1;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) q0[u] = __ldg(reinterpret_cast<const uint4*>(p.x + base + (int64_t)(r + u * step) * p.C));
+  }
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4));
+  __syncthreads();
+  float sc[8], sh[8];
+  {
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c0 + i) / p.cpg;
+      const float ga = gg[i] * s_rstd[g];
+      sc[i] = ga;
+      sh[i] = bb[i] - s_mean[g] * ga;
+    }
+  }
+  auto finish = [&](const uint4& q, int row) {
+    const float2 a = unpack_bf16(q.x), b2 = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float v = fmaf(f[i], sc[i], sh[i]);
-      if (ACT == TAIR_ACT_SILU) v = silu_f(v);
+      if (ACT == TAIR_ACT_SILU) v = silu_tanh(v);
       else if (ACT == TAIR_ACT_GELU) v = gelu_f(v);
       f[i] = v;
     }
-    store8(p.y + base + (int64_t)r * p.C, f);
+    store8(p.y + base + (int64_t)row * p.C, f);
   };
-  int r = r0 + rsub;
-  const int step = p.rows_per_iter;
-  for (; r + 3 * step < r1; r += 4 * step) {
-    float f[4][8];
+  if (first) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load8(p.x + base + (int64_t)(r + u * step) * p.C, f[u]);
+    for (int u = 0; u < U; ++u) finish(q0[u], r + u * step);
+    r += U * step;
+  }
+  for (; r + (U - 1) * step < r1; r += U * step) {
+    uint4 q[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) finish(f[u], r + u * step);
+    for (int u = 0; u < U; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(p.x + base + (int64_t)(r + u * step) * p.C));
+#pragma unroll
+    for (int u = 0; u < U; ++u) finish(q[u], r + u * step);
   }
   for (; r < r1; r += step) {
-    float f[8];
-    load8(p.x + base + (int64_t)r * p.C, f);
-    finish(f, r);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.x + base + (int64_t)r * p.C));
+    finish(q, r);
+  }
+}
+
+// Per-row LayerNorm statistics only: out[m] = (mean, rstd) of x[m, :C].  The normalisation itself is folded into the
+// GEMM that consumes the LayerNorm output (tair_epilogue.ln_row_stats / ln_col_sum): the activation is read once
+// (2 B per element) and never re-written.  One warp per row, values in registers, two-pass mean / variance.
+template <int MAXV, int R>   // 16-byte vectors per lane and row; rows per warp (all their loads are issued up front)
+__global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float2* __restrict__ out, int M, int C,
+                                 float eps) {
+  pdl_grid_sync();
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  const int lane = threadIdx.x & 31;
+  if (row0 >= M) return;
+  const int nvec = C >> 3;
+  uint4 raw[R][MAXV];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int row = row0 + rr < M ? row0 + rr : M - 1;   // clamp: rows past the end are loaded but not written
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      raw[rr][k] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * ldx + vi * 8)) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  float s[R], q[R];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
+      acc += ((a.x + a.y) + (b2.x + b2.y)) + ((c.x + c.y) + (d.x + d.y));   // padding vectors are zero
+    }
+    s[rr] = acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const float mean = s[rr] / (float)C;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      if (lane + k * 32 < nvec) {
+        const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
+        const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dd = f[i] - mean;
+          acc = fmaf(dd, dd, acc);
+        }
+      }
+    }
+    q[rr] = acc;
+    s[rr] = mean;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) q[rr] += __shfl_xor_sync(0xffffffffu, q[rr], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+      if (row0 + rr < M) out[row0 + rr] = make_float2(s[rr], rsqrtf(q[rr] / (float)C + eps));
   }
 }
 
@@ -173,6 +269,7 @@ template <int MAXV>  // max 16-byte vectors per lane
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
                                  int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  int M, int C, float eps) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -230,6 +327,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld
 __global__ void layernorm_ragged_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
                                         int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
                                         int M, int C, int Cv, float eps) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -298,7 +396,7 @@ extern "C" int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, c
   p.gamma = gamma; p.beta = beta; p.ws = reinterpret_cast<float*>(workspace);
   p.B = B; p.HW = HW; p.C = C; p.G = groups; p.cpg = cpg; p.eps = eps; p.act = act;
   p.vec_per_row = C / 8;
-  TAIR_REQUIRE(p.vec_per_row <= 1024, "groupnorm: C too large (%d)", C);
+  TAIR_REQUIRE(p.vec_per_row <= 320, "groupnorm: C too large (%d > 2560)", C);
   int rpi = 320 / p.vec_per_row;
   if (rpi < 1) rpi = 1;
   if (rpi > HW) rpi = HW;
@@ -317,14 +415,54 @@ extern "C" int tair_groupnorm_nhwc(const void* x, void* y, const float* gamma, c
   p.slabs = (HW + p.rows_per_slab - 1) / p.rows_per_slab;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(p.slabs, B);
-  gn_stats_kernel<<<grid, threads, 0, st>>>(p);
+  // loads in flight per thread: the whole slab share when it is at most 16 rows per thread (the 64x64 / 32x32 levels)
+  const int rows_per_thread = (p.rows_per_slab + rpi - 1) / rpi;
+  static int u_cfg = -1;
+  if (u_cfg < 0) { const char* e = getenv("TAIR_GN_UNROLL"); u_cfg = e ? atoi(e) : 0; }   // probe
+  const int U = u_cfg > 0 ? u_cfg : (rows_per_thread >= 16 ? 16 : (rows_per_thread >= 8 ? 8 : (rows_per_thread >= 4 ? 4 : 1)));
+  if (U >= 16) TAIR_LAUNCH((gn_stats_kernel<16>), grid, threads, 0, st, p);
+  else if (U >= 8) TAIR_LAUNCH((gn_stats_kernel<8>), grid, threads, 0, st, p);
+  else if (U >= 4) TAIR_LAUNCH((gn_stats_kernel<4>), grid, threads, 0, st, p);
+  else TAIR_LAUNCH((gn_stats_kernel<1>), grid, threads, 0, st, p);
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
-  if (act == TAIR_ACT_SILU) gn_apply_kernel<TAIR_ACT_SILU><<<grid, threads, 0, st>>>(p);
-  else if (act == TAIR_ACT_GELU) gn_apply_kernel<TAIR_ACT_GELU><<<grid, threads, 0, st>>>(p);
-  else gn_apply_kernel<TAIR_ACT_NONE><<<grid, threads, 0, st>>>(p);
+  const int UA = U >= 8 ? 8 : (U >= 4 ? 4 : 1);
+#define TAIR_GN_APPLY(ACT_)                                                                   \
+  do {                                                                                        \
+    if (UA == 8) TAIR_LAUNCH((gn_apply_kernel<ACT_, 8>), grid, threads, 0, st, p);            \
+    else if (UA == 4) TAIR_LAUNCH((gn_apply_kernel<ACT_, 4>), grid, threads, 0, st, p);       \
+    else TAIR_LAUNCH((gn_apply_kernel<ACT_, 1>), grid, threads, 0, st, p);                    \
+  } while (0)
+  if (act == TAIR_ACT_SILU) TAIR_GN_APPLY(TAIR_ACT_SILU);
+  else if (act == TAIR_ACT_GELU) TAIR_GN_APPLY(TAIR_ACT_GELU);
+  else TAIR_GN_APPLY(TAIR_ACT_NONE);
+#undef TAIR_GN_APPLY
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   return check_launch("gn_apply_kernel");
+}
+
+extern "C" int tair_row_stats(const void* x, int64_t ldx, float* out, int32_t M, int32_t C, float eps, void* stream) {
+  TAIR_REQUIRE(x && out, "row_stats: NULL pointer");
+  TAIR_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && C <= 2048, "row_stats: C must be a multiple of 8 and <= 2048 (C=%d)", C);
+  TAIR_REQUIRE(ldx % 8 == 0 && ldx >= C, "row_stats: bad row stride");
+  TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) == 0,
+               "row_stats: x must be 16-byte and out 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int warps_cfg = -1;
+  if (warps_cfg < 0) { const char* e = getenv("TAIR_RS_WARPS"); warps_cfg = e ? atoi(e) : 8; }   // probe
+  const int warps = warps_cfg >= 1 && warps_cfg <= 32 ? warps_cfg : 8;
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  float2* op = reinterpret_cast<float2*>(out);
+  const int nvec = C / 8;
+  // rows per warp: enough 16-byte loads in flight per lane (4-8) to cover the memory latency of a read-only kernel
+  auto grid_for = [&](int R) { const int rows_per_cta = warps * R; return (M + rows_per_cta - 1) / rows_per_cta; };
+  if (nvec <= 32) TAIR_LAUNCH((row_stats_kernel<1, 4>), grid_for(4), warps * 32, 0, st, xp, ldx, op, M, C, eps);
+  else if (nvec <= 64) TAIR_LAUNCH((row_stats_kernel<2, 4>), grid_for(4), warps * 32, 0, st, xp, ldx, op, M, C, eps);
+  else if (nvec <= 96) TAIR_LAUNCH((row_stats_kernel<3, 2>), grid_for(2), warps * 32, 0, st, xp, ldx, op, M, C, eps);
+  else if (nvec <= 160) TAIR_LAUNCH((row_stats_kernel<5, 1>), grid_for(1), warps * 32, 0, st, xp, ldx, op, M, C, eps);
+  else TAIR_LAUNCH((row_stats_kernel<8, 1>), grid_for(1), warps * 32, 0, st, xp, ldx, op, M, C, eps);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("row_stats_kernel");
 }
 
 extern "C" int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
@@ -342,10 +480,10 @@ extern "C" int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, 
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const int nvec = C / 8;
-  if (nvec <= 32) layernorm_kernel<1><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
-  else if (nvec <= 64) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
-  else if (nvec <= 160) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
-  else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(xp, ldx, yp, ldy, gamma, beta, M, C, eps);
+  if (nvec <= 32) TAIR_LAUNCH((layernorm_kernel<1>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
+  else if (nvec <= 64) TAIR_LAUNCH((layernorm_kernel<2>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
+  else if (nvec <= 160) TAIR_LAUNCH((layernorm_kernel<5>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
+  else TAIR_LAUNCH((layernorm_kernel<8>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("layernorm_kernel");
 }
@@ -359,7 +497,7 @@ extern "C" int tair_layernorm_ragged(const void* x, int64_t ldx, void* y, int64_
   TAIR_REQUIRE((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(y) % 16) == 0,
                "layernorm_ragged: tensors must be 16-byte aligned");
   const int warps = 8;
-  layernorm_ragged_kernel<<<(M + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  TAIR_LAUNCH((layernorm_ragged_kernel), (M + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, gamma, beta, M, C, C_valid, eps);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("layernorm_ragged_kernel");

@@ -25,6 +25,7 @@ __device__ __forceinline__ int clip8(int v) {
 __global__ void resize_h_kernel(const uint8_t* __restrict__ img, int Wp, const int32_t* __restrict__ origins,
                                 const int32_t* __restrict__ bounds, const int32_t* __restrict__ coeffs, int ksize,
                                 int tile, int out, uint8_t* __restrict__ tmp, long total) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int ox = (int)(idx % out);
@@ -47,6 +48,7 @@ __global__ void resize_h_kernel(const uint8_t* __restrict__ img, int Wp, const i
 __global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, const int32_t* __restrict__ bounds,
                                 const int32_t* __restrict__ coeffs, int ksize, int tile, int out,
                                 float* __restrict__ dst, long total) {
+  pdl_grid_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int ox = (int)(idx % out);
@@ -81,12 +83,12 @@ extern "C" int tair_tiles_bicubic_u8(const void* image, int32_t Hp, int32_t Wp, 
                "tiles_bicubic: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long t1 = (long)P * tile * out, t2 = (long)P * out * out;
-  resize_h_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(image), Wp, origins,
+  TAIR_LAUNCH((resize_h_kernel), (unsigned)((t1 + 255) / 256), 256, 0, st, reinterpret_cast<const uint8_t*>(image), Wp, origins,
                                                                  bounds, coeffs, ksize, tile, out,
                                                                  reinterpret_cast<uint8_t*>(tmp), t1);
   int rc = check_launch("resize_h_kernel");
   if (rc) return rc;
-  resize_v_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(tmp), bounds, coeffs,
+  TAIR_LAUNCH((resize_v_kernel), (unsigned)((t2 + 255) / 256), 256, 0, st, reinterpret_cast<const uint8_t*>(tmp), bounds, coeffs,
                                                                  ksize, tile, out, dst, t2);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   return check_launch("resize_v_kernel");

@@ -9,10 +9,16 @@ but operates on channels-last bf16 token matrices [B*HW, C] and launches:
     to_q|to_k|to_v of attn1        ONE tair_gemm_bf16 with the three weights stacked ([3C, C])
     to_k|to_v of attn2             hoisted: all blocks' context projections are one GEMM per network per step
     softmax(QK^T/8)V               tair_attention_bf16 (tcgen05 flash attention, head_dim 64)
-    LayerNorm                      tair_layernorm
+    LayerNorm                      folded into the GEMM that consumes it: norm1 -> attn1 q|k|v, norm2 -> attn2 to_q,
+                                   norm3 -> GEGLU.  The GEMM reads the RAW rows with weights W * gamma and rescales its
+                                   accumulator per row in the epilogue, rstd * (acc - mean * sum_k W'[n,k]) + (b + W beta);
+                                   only the per-row (mean, rstd) are computed beforehand (tair_row_stats: one 2 B/element
+                                   read instead of LayerNorm's read + write).  Mathematically identical to
+                                   Linear(LayerNorm(x)); the normalised tensor is never materialised.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -29,6 +35,18 @@ def geglu_tile(n_rows: int) -> int:
     if n_rows % 128 == 0:
         return 128
     raise ValueError(f"GEGLU projection with {n_rows} rows cannot be tiled (needs a multiple of 128)")
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], ln: "LayerNorm"):
+    """Linear(LayerNorm(x)) == rstd * (x @ (W*gamma)^T - mean * colsum) + (b + W @ beta): -> (W*gamma as bf16 [N,K],
+    bias' fp32 [N], colsum fp32 [N] taken over the bf16-rounded folded weight so that it cancels the accumulator exactly)."""
+    w32 = w.detach().float()
+    g, beta = ln.weight.detach().float(), ln.bias.detach().float()
+    wf = (w32 * g[None, :]).to(BF16).contiguous()
+    bias = w32 @ beta
+    if b is not None:
+        bias = bias + b.detach().float()
+    return wf, bias.contiguous(), wf.float().sum(1).contiguous()
 
 
 def interleave_geglu(w: torch.Tensor, b: torch.Tensor):
@@ -57,7 +75,21 @@ class GEGLU(nn.Module):
             self._pk, self._pk_stamp = (w, b), st
         return self._pk
 
-    def forward(self, x2d: torch.Tensor) -> torch.Tensor:
+    def _packed_ln(self, ln):
+        st = (self.proj._stamp(), ln._stamp())
+        if getattr(self, "_ln_stamp", None) != st:
+            with torch.no_grad():
+                wf, bias, _ = fold_layernorm(self.proj.weight, self.proj.bias, ln)
+                w, b = interleave_geglu(wf, bias)
+                self._ln_pk = (w, b, w.float().sum(1).contiguous())
+            self._ln_stamp = st
+        return self._ln_pk
+
+    def forward(self, x2d: torch.Tensor, ln=None, stats=None) -> torch.Tensor:
+        """``ln`` (a LayerNorm module) + ``stats`` = row_stats(x2d): computes GEGLU(ln(x2d)) from the raw rows."""
+        if ln is not None:
+            w, b, cs = self._packed_ln(ln)
+            return ops.gemm(x2d, w, bias=b, act=ops.ACT_GEGLU, ln=(stats, cs))
         w, b = self._packed()
         return ops.gemm(x2d, w, bias=b, act=ops.ACT_GEGLU)
 
@@ -70,8 +102,8 @@ class FeedForward(nn.Module):
         inner = dim * mult
         self.net = nn.Sequential(GEGLU(dim, inner), nn.Dropout(0.0), Linear(inner, dim))
 
-    def forward(self, x2d: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
-        return self.net[2](self.net[0](x2d), residual=residual)
+    def forward(self, x2d: torch.Tensor, residual: torch.Tensor, ln=None, stats=None) -> torch.Tensor:
+        return self.net[2](self.net[0](x2d, ln=ln, stats=stats), residual=residual)
 
 
 class CrossAttention(nn.Module):
@@ -109,18 +141,33 @@ class CrossAttention(nn.Module):
             self._kv_stamp = st
         return self._kv
 
+    def _folded(self, ln):
+        """Query-side projection (q|k|v stacked for self-attention, to_q for cross-attention) with ``ln`` folded in."""
+        st = (self._stamp(), ln._stamp())
+        if getattr(self, "_fold_stamp", None) != st:
+            with torch.no_grad():
+                w = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0) if self.is_self else self.to_q.weight
+                self._fold = fold_layernorm(w, None, ln)
+            self._fold_stamp = st
+        return self._fold
+
     def forward(self, x2d: torch.Tensor, B: int, residual: torch.Tensor, kv: Optional[torch.Tensor] = None,
-                Lk: int = 0) -> torch.Tensor:
-        """x2d [B*L, C]; kv = precomputed [B*Lk, 2*inner] context projection for cross attention."""
+                Lk: int = 0, ln=None) -> torch.Tensor:
+        """x2d [B*L, C]; kv = precomputed [B*Lk, 2*inner] context projection for cross attention.  With ``ln`` (a
+        LayerNorm module) x2d holds the RAW rows and the normalisation is folded into the projection GEMM."""
         L = x2d.shape[0] // B
         C = self.inner
         scale = self.dim_head ** -0.5
+        lnk = None
+        if ln is not None:
+            wf, bf, cs = self._folded(ln)
+            lnk = (ops.row_stats(x2d, ln.eps), cs)
         if kv is None:
-            qkv = ops.gemm(x2d, self.qkv_weight())
+            qkv = ops.gemm(x2d, wf, bias=bf, ln=lnk) if ln is not None else ops.gemm(x2d, self.qkv_weight())
             a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B=B, H=self.heads, Lq=L, Lk=L,
                               head_dim=self.dim_head, scale=scale)
         else:
-            q = self.to_q(x2d)
+            q = ops.gemm(x2d, wf, bias=bf, ln=lnk) if ln is not None else self.to_q(x2d)
             a = ops.attention(q, kv[:, :C], kv[:, C:], B=B, H=self.heads, Lq=L, Lk=Lk, head_dim=self.dim_head,
                               scale=scale)
         return self.to_out[0](a, residual=residual)
@@ -135,11 +182,16 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
         self.attn2 = CrossAttention(dim, context_dim, n_heads, d_head)
         self.norm1, self.norm2, self.norm3 = LayerNorm(dim), LayerNorm(dim), LayerNorm(dim)
+        self.fold_layernorm = os.environ.get("TAIR_FOLD_LN", "1") != "0"   # 0: the separate LayerNorm kernel (A/B probe)
 
     def forward(self, x2d: torch.Tensor, B: int, ctx_kv: torch.Tensor, Lk: int) -> torch.Tensor:
-        x2d = self.attn1(self.norm1(x2d), B, residual=x2d)
-        x2d = self.attn2(self.norm2(x2d), B, residual=x2d, kv=ctx_kv, Lk=Lk)
-        return self.ff(self.norm3(x2d), residual=x2d)
+        if not self.fold_layernorm:
+            x2d = self.attn1(self.norm1(x2d), B, residual=x2d)
+            x2d = self.attn2(self.norm2(x2d), B, residual=x2d, kv=ctx_kv, Lk=Lk)
+            return self.ff(self.norm3(x2d), residual=x2d)
+        x2d = self.attn1(x2d, B, residual=x2d, ln=self.norm1)
+        x2d = self.attn2(x2d, B, residual=x2d, kv=ctx_kv, Lk=Lk, ln=self.norm2)
+        return self.ff(x2d, residual=x2d, ln=self.norm3, stats=ops.row_stats(x2d, self.norm3.eps))
 
 
 class SpatialTransformer(nn.Module):

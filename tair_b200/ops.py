@@ -130,8 +130,9 @@ def _make_epilogue(out, M, n_out, bias, residual, rowgroup, rows_per_group, act)
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup=None, rows_per_group=0,
-         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, out_dtype=BF16) -> torch.Tensor:
-    """``epilogue(a @ w.T)``; a [M,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
+         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, out_dtype=BF16, ln=None) -> torch.Tensor:
+    """``epilogue(a @ w.T)``; a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).
+    ``ln = (row_stats [M,2] fp32, col_sum [N] fp32)``: LayerNorm folded in (see tair_epilogue.ln_row_stats)."""
     _cuda(a, "a", BF16), _cuda(w, "w", BF16)
     a2, lda = _rows(a, "a")
     w2, ldw = _rows(w, "w")
@@ -143,6 +144,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
     e = _make_epilogue(out, M, n_out, bias, residual, rowgroup, rows_per_group, act)
+    if ln is not None:
+        rs, cs = ln
+        _cuda(rs, "ln row_stats", torch.float32), _cuda(cs, "ln col_sum", torch.float32)
+        if tuple(rs.shape) != (M, 2) or cs.numel() != N or not (rs.is_contiguous() and cs.is_contiguous()):
+            raise TairError("gemm: ln = (row_stats [M,2], col_sum [N]) contiguous fp32 expected")
+        e.ln_row_stats, e.ln_col_sum = rs.data_ptr(), cs.data_ptr()
     with _timed("gemm", 2.0 * M * N * K, (M, N, K, act)):
         rc = _lib.lib().tair_gemm_bf16(a2.data_ptr(), lda, w2.data_ptr(), ldw, M, N, K, C.byref(e), _stream())
     _lib.check(rc, "tair_gemm_bf16")
@@ -260,6 +267,18 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, group
         rc = _lib.lib().tair_groupnorm_nhwc(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, HW, C,
                                             groups, float(eps), act, ws.data_ptr(), _stream())
     _lib.check(rc, "tair_groupnorm_nhwc")
+    return out
+
+
+def row_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per row of a bf16 [M,C] matrix -> fp32 [M,2]; the LayerNorm that owns them is folded into its
+    consumer GEMM (``gemm(..., ln=(stats, col_sum))``)."""
+    _cuda(x, "x", BF16)
+    x2, ldx = _rows(x, "x")
+    out = torch.empty((x2.shape[0], 2), device=x.device, dtype=torch.float32)
+    with _timed("layernorm_stats", 4.0 * x2.numel(), tuple(x2.shape)):   # algorithmic bytes of the LayerNorm it replaces
+        rc = _lib.lib().tair_row_stats(x2.data_ptr(), ldx, out.data_ptr(), x2.shape[0], x2.shape[1], float(eps), _stream())
+    _lib.check(rc, "tair_row_stats")
     return out
 
 
@@ -568,3 +587,29 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
     rc = _lib.lib().tair_transpose_bf16(x3.data_ptr(), Cc, R * Cc, out.data_ptr(), R, R * Cc, Bn, R, Cc, _stream())
     _lib.check(rc, "tair_transpose_bf16")
     return out if x.dim() == 3 else out[0]
+
+
+def testr_postprocess(pred_logits: torch.Tensor, pred_ctrl_points: torch.Tensor, pred_texts: torch.Tensor,
+                      image_w: float, image_h: float):
+    """Dense TESTR outputs (B,Q,P,1) / (B,Q,P,2) / (B,Q,L,V) fp32 -> (scores fp32 [B,Q], polygons fp32 [B,Q,2P] in pixels,
+    recs uint8 [B,Q,L], the packed uint8 buffer the three are views of) in one kernel; see tair_testr_postprocess."""
+    for t, n in ((pred_logits, "pred_logits"), (pred_ctrl_points, "pred_ctrl_points"), (pred_texts, "pred_texts")):
+        _cuda(t, n, torch.float32)
+        if not t.is_contiguous():
+            raise TairError(f"testr_postprocess: {n} must be contiguous")
+    B, Q, P = pred_ctrl_points.shape[:3]
+    L, V = pred_texts.shape[2:]
+    if pred_logits.numel() != B * Q * P or pred_ctrl_points.shape[3] != 2 or tuple(pred_texts.shape[:2]) != (B, Q):
+        raise TairError("testr_postprocess: inconsistent shapes (one class per control point expected)")
+    dev = pred_logits.device
+    # one packed buffer (scores | polygons | recs) so that the caller brings everything to the host in a single copy
+    n_s, n_p = B * Q * 4, B * Q * 2 * P * 4
+    pack = torch.empty((n_s + n_p + B * Q * L,), device=dev, dtype=torch.uint8)
+    scores = pack[:n_s].view(torch.float32).view(B, Q)
+    polys = pack[n_s:n_s + n_p].view(torch.float32).view(B, Q, 2 * P)
+    recs = pack[n_s + n_p:].view(B, Q, L)
+    rc = _lib.lib().tair_testr_postprocess(pred_logits.data_ptr(), pred_ctrl_points.data_ptr(), pred_texts.data_ptr(),
+                                           scores.data_ptr(), polys.data_ptr(), recs.data_ptr(), B * Q, P, L, V,
+                                           float(image_w), float(image_h), _stream())
+    _lib.check(rc, "tair_testr_postprocess")
+    return scores, polys, recs, pack

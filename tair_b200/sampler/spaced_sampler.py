@@ -270,12 +270,16 @@ class SpacedSampler(Sampler):
                     x, feats = self.p_sample(model, x, model_t, t, cond, uncond, scale, noise=self._noise(i, x))
                     if ours:
                         dense = ts_model.testr(feats)
-                if dense is not None:
-                    results = ts_model.inference(dense["pred_logits"], dense["pred_ctrl_points"], dense["pred_texts"],
-                                                 [(512, 512)] * bs)
+                results = None
+                if dense is not None and self.trace is None and hasattr(ts_model, "detect_host"):
+                    texts, polys = ts_model.detect_host(dense, (512, 512))     # one kernel + one D2H for the whole batch
                 else:
-                    _, results = ts_model(feats, None, mode)
-                texts, polys = decode_texts(results)                       # one D2H copy for the whole batch
+                    if dense is not None:
+                        results = ts_model.inference(dense["pred_logits"], dense["pred_ctrl_points"], dense["pred_texts"],
+                                                     [(512, 512)] * bs)
+                    else:
+                        _, results = ts_model(feats, None, mode)
+                    texts, polys = decode_texts(results)
                 prompts = [build_prompt(tx, style) for tx in texts]
                 cond["c_txt"] = pure_cldm.clip.encode(prompts if bs > 1 else prompts[0])   # mutated in place like :317
                 ts_results.append(dict(timestep=cur, pred_texts=texts[0], pred_prompt=prompts[0], pred_polys=polys[0],

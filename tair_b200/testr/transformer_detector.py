@@ -7,9 +7,11 @@ from __future__ import annotations
 from types import SimpleNamespace
 from typing import List, Optional, Sequence
 
+import numpy as np
 import torch
 from torch import nn
 
+from .. import ops
 from .models import TESTR
 from .structures import Instances
 
@@ -41,6 +43,20 @@ class TransformerDetector(nn.Module):
         image_sizes = [(512, 512) for _ in range(bs)]
         results = self.inference(output["pred_logits"], output["pred_ctrl_points"], output["pred_texts"], image_sizes)
         return None, results
+
+    def detect_host(self, dense, image_size=(512, 512)):
+        """The sampler's view of ``inference`` (spaced_sampler.py:294-306 only reads ``polygons`` and ``recs``): one
+        post-processing kernel over all tiles x queries, ONE device->host copy, thresholding and string decode on the host.
+        -> (texts [B][k] str, polys [B][k] int32 (16,2)); same detections, order and values as ``inference`` + ``decode``."""
+        from ..prompt import texts_and_polys
+        scores, polys, recs, pack = ops.testr_postprocess(dense["pred_logits"].contiguous(), dense["pred_ctrl_points"].contiguous(),
+                                                          dense["pred_texts"].contiguous(), float(image_size[1]), float(image_size[0]))
+        B, Q = scores.shape
+        n_s, n_p = scores.numel() * 4, polys.numel() * 4
+        host = pack.cpu().numpy()
+        return texts_and_polys(host[:n_s].view(np.float32).reshape(B, Q),
+                               host[n_s:n_s + n_p].view(np.float32).reshape(B, Q, -1),
+                               host[n_s + n_p:].reshape(B, Q, -1), self.test_score_threshold)
 
     def inference(self, ctrl_point_cls, ctrl_point_coord, text_pred, image_sizes) -> List[Instances]:
         """transformer_detector.py:123-152: softmax over the vocabulary, score = sigmoid(mean point logit),

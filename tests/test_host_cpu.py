@@ -208,3 +208,23 @@ def test_reference_make_tiled_fn_agrees(tmp_path):
     fn = lambda t: torch.tanh(t) * 3   # noqa: E731
     for size, stride in ((16, 8), (16, 12), (32, 20)):
         assert torch.equal(make_tiled_fn(fn, size, stride, progress=False)(x), ref_tiled(fn, size, stride, progress=False)(x))
+
+
+def test_vectorised_decode_matches_scalar_decode():
+    import numpy as np
+    from tair_b200 import prompt as P
+    rng = np.random.default_rng(0)
+    recs = rng.integers(0, 97, (500, 25))
+    recs[::7, 3] = 96          # early terminator
+    recs[5] = rng.integers(0, 95, 25)   # no terminator at all
+    recs[6, 0] = 95            # empty string
+    assert P.decode_batch(recs) == [P.decode(r) for r in recs]
+    assert P.decode_batch(recs.astype(np.uint8)) == [P.decode(r) for r in recs]
+    assert P.decode_batch(np.zeros((0, 25), np.uint8)) == []
+    scores = rng.random((2, 100)).astype(np.float32)
+    polys = (rng.random((2, 100, 32)) * 512).astype(np.float32)
+    texts, pg = P.texts_and_polys(scores, polys, recs[:200].reshape(2, 100, 25), 0.5)
+    for b in range(2):
+        keep = scores[b] >= 0.5
+        assert texts[b] == [P.decode(r) for r in recs[:200].reshape(2, 100, 25)[b][keep]]
+        assert all(np.array_equal(a, p.reshape(16, 2).astype(np.int32)) for a, p in zip(pg[b], polys[b][keep]))

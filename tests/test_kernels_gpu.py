@@ -90,7 +90,9 @@ def test_conv3x3_fused_epilogue(ops):
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk", [(1, 1, 128, 128), (2, 5, 1024, 1024), (2, 10, 1024, 77), (3, 20, 64, 64),
-                                       (3, 20, 64, 77), (1, 3, 200, 333), (1, 5, 4096, 4096)])
+                                       (3, 20, 64, 77), (1, 3, 200, 333), (1, 5, 4096, 4096),
+                                       # short contexts take the key/value-stationary kernel: many / few / ragged query tiles
+                                       (4, 5, 4096, 77), (2, 20, 256, 77), (1, 5, 200, 50), (5, 2, 1300, 80), (2, 3, 128, 1)])
 def test_attention(ops, B, H, Lq, Lk):
     C = H * 64
     q, k, v = rn(B * Lq, C, scale=1.5).bfloat16(), rn(B * Lk, C, scale=1.5, seed=1).bfloat16(), rn(B * Lk, C, seed=2).bfloat16()
@@ -222,3 +224,72 @@ def test_blend_tiles_fixture_and_ragged_list(ops, golden):
     short = [t[None] for t in tl[:4].cpu()]
     ref = tiles.merge_tiles(short, (oh, ow))
     assert torch.equal(ops.blend_tiles(tl[:4].contiguous(), 2, 3, 64, 4 * oh, 4 * ow).cpu(), ref)
+
+
+@pytest.mark.parametrize("M,C,N,act", [(300, 320, 960, "none"), (1000, 640, 640, "none"), (257, 64, 512, "geglu"),
+                                       (4096, 1280, 10240, "geglu")])
+def test_layernorm_folded_into_gemm(cuda_lib, M, C, N, act):
+    """Linear(LayerNorm(x)) from the raw rows: tair_row_stats + the ln_row_stats / ln_col_sum epilogue against fp32 torch,
+    with a row offset far from zero (mean >> std is where the folded form could cancel badly)."""
+    import torch.nn.functional as F
+    from tair_b200 import ops
+    from tair_b200.model.attention import fold_layernorm, interleave_geglu
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn(M, C, device="cuda", generator=g) * 1.5 + 3.0 * torch.randn(M, 1, device="cuda", generator=g)).bfloat16()
+    ln = torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.3 * torch.randn(C, device="cuda", generator=g))
+        ln.bias.copy_(0.2 * torch.randn(C, device="cuda", generator=g))
+    w = torch.randn(N, C, device="cuda", generator=g) / C ** 0.5
+    b = 0.1 * torch.randn(N, device="cuda", generator=g)
+    ln._stamp = lambda: 0
+    wf, bias, cs = fold_layernorm(w, b, ln)
+    stats = ops.row_stats(x, ln.eps)
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.mean(1), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], (xf.var(1, unbiased=False) + ln.eps).rsqrt(), rtol=1e-4)
+    y_ref = F.linear(F.layer_norm(xf, (C,), ln.weight, ln.bias, ln.eps), w, b)
+    if act == "geglu":
+        wi, bi = interleave_geglu(wf, bias)
+        out = ops.gemm(x, wi, bias=bi, act=ops.ACT_GEGLU, ln=(stats, wi.float().sum(1).contiguous()))
+        v, gate = y_ref.chunk(2, dim=-1)
+        y_ref = v * F.gelu(gate)
+    else:
+        out = ops.gemm(x, wf, bias=bias, ln=(stats, cs))
+    assert rel(out, y_ref) < 1.5e-2
+    # and it agrees with the unfused kernels (LayerNorm kernel -> GEMM) to bf16 round-off
+    y_unf = ops.layernorm(x, ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous(), eps=ln.eps)
+    if act != "geglu":
+        assert rel(out, ops.gemm(y_unf, w.bfloat16().contiguous(), bias=b.contiguous())) < 1.5e-2
+
+
+def test_gelu_epilogue_matches_erf_gelu(cuda_lib):
+    """The A&S erf used by the GELU / GEGLU epilogues is exact to fp32 round-off over the whole range."""
+    import torch.nn.functional as F
+    from tair_b200 import ops
+    x = torch.linspace(-9, 9, 4096 * 64, device="cuda").view(4096, 64).bfloat16()
+    eye = torch.eye(64, device="cuda").bfloat16()
+    out = ops.gemm(x, eye, act=ops.ACT_GELU, out_dtype=torch.float32)
+    assert (out - F.gelu(x.float())).abs().max().item() < 2e-6
+
+
+def test_geglu_gate_activation_tolerance(cuda_lib):
+    """The GEGLU epilogue evaluates the gate's GELU in tanh form through the hardware tanh (csrc/common.cuh gelu_tanh_f):
+    absolute deviation from the exact erf GELU <= 1e-3 everywhere (4.8e-4 analytic + tanh.approx), i.e. well below the bf16
+    rounding of the product it feeds."""
+    import torch.nn.functional as F
+    from tair_b200 import ops
+    from tair_b200.model.attention import interleave_geglu
+    n = 128
+    gate = torch.linspace(-8, 8, 2048 * n, device="cuda").view(2048, n)
+    # value weights = 0 with bias 1 (value == 1), gate weights = identity on the first n inputs
+    a = gate.bfloat16()
+    w = torch.zeros(2 * n, n, device="cuda")
+    w[n:] = torch.eye(n, device="cuda")
+    b = torch.cat([torch.ones(n, device="cuda"), torch.zeros(n, device="cuda")])
+    wi, bi = interleave_geglu(w.bfloat16(), b)
+    out = ops.gemm(a, wi, bias=bi, act=ops.ACT_GEGLU, out_dtype=torch.float32)
+    ref = F.gelu(a.float())
+    assert (out - ref).abs().max().item() < 1e-3
+    out_bf = ops.gemm(a, wi, bias=bi, act=ops.ACT_GEGLU)
+    assert (out_bf.float() - ref).abs().max().item() < 1e-3 + 2 ** -8 * ref.abs().max().item()

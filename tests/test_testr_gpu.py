@@ -209,3 +209,18 @@ def test_detector_instances_vs_reference_fixture(detector, golden):
     assert diff.float().mean().item() < 0.25
     print(f"instances: {int(ref_keep.sum())} reference / {int(keep.sum())} product / {int(both.sum())} shared; "
           f"{int(diff.sum())} of {diff.numel()} characters differ (all within margin)")
+
+
+def test_detect_host_equals_inference_plus_decode(detector):
+    """The one-kernel post-processing + single D2H used inside val_sample gives the same detections, strings and int32
+    polygons as TransformerDetector.inference (transformer_detector.py:123-152) followed by the per-instance decode."""
+    from tair_b200.prompt import decode_texts
+    m, _ = detector
+    dense = m.testr(feats_for(2))
+    res = m.inference(dense["pred_logits"], dense["pred_ctrl_points"], dense["pred_texts"], [(512, 512)] * 2)
+    texts_ref, polys_ref = decode_texts(res)
+    texts, polys = m.detect_host(dense, (512, 512))
+    assert texts == texts_ref
+    for a, b in zip(polys, polys_ref):
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert sum(len(t) for t in texts) > 0
