@@ -244,19 +244,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
-      if (j > 0) {                // P V(j-1) must have retired before O is rescaled or P is overwritten
-        mbar_wait(p_free, (j - 1) & 1);
-        tc_fence_after();
-      }
       // lazy running maximum: move it only when this block exceeds it by more than 8 (in log2 units)
       const float m_blk = mx * c;
       const bool bump = m_blk > m_run + 8.f;
-      if (__any_sync(0xffffffffu, bump)) {
+      const bool any_bump = __any_sync(0xffffffffu, bump);
+      float alpha = 1.f;
+      if (any_bump) {
         const float m_new = bump ? m_blk : m_run;
-        const float alpha = ex2_approx(m_run - m_new);   // 1 for lanes that keep their maximum, 0 on the first block
+        alpha = ex2_approx(m_run - m_new);   // 1 for lanes that keep their maximum, 0 on the first block
         l_run *= alpha;
         m_run = m_new;
-        if (j > 0) {  // rescale the accumulated O row in TMEM
+      }
+      // P = exp2(S*c - m) -> packed bf16, kept in REGISTERS (the S values die as they are consumed) and written to the P
+      // columns only after P V(j-1) has retired: the tensor pipe is shared with the co-resident CTA, so that MMA can sit
+      // behind 400+ cycles of foreign work, and waiting for it before the exponentials left the MUFU idle.
+      // Two straight-line copies: the unmasked one (all blocks but the last / the causal diagonal) carries no
+      // per-element compare+select — they were 2 of 7 instructions per element when the mask was predicated in.
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+      uint32_t pk[AT_BN / 2];
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < AT_BN; i += 4) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sv[i + 0]), c, -m_run));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -m_run));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), c, -m_run));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(sv[i + 3]), c, -m_run));
+          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+          pk[(i >> 1) + 0] = pack_bf16(e0, e1);
+          pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < AT_BN; i += 4) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(sv[i + 0]), c, -m_run));
+          float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -m_run));
+          float e2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), c, -m_run));
+          float e3 = ex2_approx(fmaf(__uint_as_float(sv[i + 3]), c, -m_run));
+          if (i + 0 >= kvalid || i + 0 < klo) e0 = 0.f;
+          if (i + 1 >= kvalid || i + 1 < klo) e1 = 0.f;
+          if (i + 2 >= kvalid || i + 2 < klo) e2 = 0.f;
+          if (i + 3 >= kvalid || i + 3 < klo) e3 = 0.f;
+          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+          pk[(i >> 1) + 0] = pack_bf16(e0, e1);
+          pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+        }
+      }
+      if (j > 0) {                // P V(j-1) must have retired before O is rescaled or P is overwritten
+        mbar_wait(p_free, (j - 1) & 1);
+        tc_fence_after();
+        if (any_bump) {           // rescale the accumulated O row in TMEM
 #pragma unroll
           for (int half = 0; half < 4; ++half) {
             uint32_t ov[16];
@@ -268,46 +304,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-      // P = exp2(S*c - m) -> packed bf16 -> TMEM columns [cc/2, cc/2+16), i.e. over S columns already in registers.
-      // Two straight-line copies: the unmasked one (all blocks but the last / the causal diagonal) carries no
-      // per-element compare+select — they were 2 of 7 instructions per element when the mask was predicated in.
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-      if (full) {
 #pragma unroll
-        for (int cc = 0; cc < AT_BN; cc += 32) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 0]), c, -m_run));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
-            const float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
-            const float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
-            ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
-            pk[(i >> 1) + 0] = pack_bf16(e0, e1);
-            pk[(i >> 1) + 1] = pack_bf16(e2, e3);
-          }
-          tmem_st_32x16(tm_P + lane_off + (cc >> 1), pk);
-        }
-      } else {
-#pragma unroll
-        for (int cc = 0; cc < AT_BN; cc += 32) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 0]), c, -m_run));
-            float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 1]), c, -m_run));
-            float e2 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 2]), c, -m_run));
-            float e3 = ex2_approx(fmaf(__uint_as_float(sv[cc + i + 3]), c, -m_run));
-            if (cc + i + 0 >= kvalid || cc + i + 0 < klo) e0 = 0.f;
-            if (cc + i + 1 >= kvalid || cc + i + 1 < klo) e1 = 0.f;
-            if (cc + i + 2 >= kvalid || cc + i + 2 < klo) e2 = 0.f;
-            if (cc + i + 3 >= kvalid || cc + i + 3 < klo) e3 = 0.f;
-            ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
-            pk[(i >> 1) + 0] = pack_bf16(e0, e1);
-            pk[(i >> 1) + 1] = pack_bf16(e2, e3);
-          }
-          tmem_st_32x16(tm_P + lane_off + (cc >> 1), pk);
-        }
+      for (int cc = 0; cc < AT_BN / 2; cc += 16) {
+        uint32_t (&chunk)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[cc]);
+        tmem_st_32x16(tm_P + lane_off + cc, chunk);
       }
       l_run += (ls0 + ls1) + (ls2 + ls3);
       tmem_st_wait();
@@ -641,7 +641,9 @@ int launch_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, con
       const double cost = (double)((pairs * cc + slots - 1) / slots) * (tpc + 1.5);
       if (cost < best - 1e-9) { best = cost; chunks = cc; }
     }
+    if (const char* e = getenv("TAIR_KVS_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= p.q_tiles) chunks = v; }   // probe
     const int tiles_per_cta = (p.q_tiles + chunks - 1) / chunks;
+    chunks = (p.q_tiles + tiles_per_cta - 1) / tiles_per_cta;
     CUtensorMap tmO;
     if ((rc = make_map(&tmO, o, ldo, H * 64, Lq, n_inner, n_outer, q_tok, q_inner, q_outer, 32))) return rc;
     TAIR_SMEM_OPTIN(attn_kvs_kernel, KS_SMEM);

@@ -199,46 +199,50 @@ __global__ void __launch_bounds__(320) gn_apply_kernel(const GnParams p) {
 // Per-row LayerNorm statistics only: out[m] = (mean, rstd) of x[m, :C].  The normalisation itself is folded into the
 // GEMM that consumes the LayerNorm output (tair_epilogue.ln_row_stats / ln_col_sum): the activation is read once
 // (2 B per element) and never re-written.  One warp per row, values in registers, two-pass mean / variance.
-template <int MAXV, int R>   // 16-byte vectors per lane and row; rows per warp (all their loads are issued up front)
+// Mapping: LPR = 2^lpr_log2 lanes share a row (lane `sub` owns vectors sub, sub + LPR, ...: every load instruction covers
+// LPR * 16 contiguous bytes per row), a warp covers 32 / LPR row groups x R2 rows each, and ALL loads of a thread
+// (VPL * R2 <= 10) are issued before the first use — the kernel is a pure read stream, its speed is bytes in flight.
+template <int VPL, int R2>
 __global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float2* __restrict__ out, int M, int C,
-                                 float eps) {
+                                 float eps, int lpr_log2) {
   pdl_grid_sync();
-  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   const int lane = threadIdx.x & 31;
-  if (row0 >= M) return;
+  const int lpr = 1 << lpr_log2;
+  const int sub = lane & (lpr - 1), rgrp = lane >> lpr_log2;
+  const int rows_per_warp = (32 >> lpr_log2) * R2;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rows_per_warp + rgrp * R2;
   const int nvec = C >> 3;
-  uint4 raw[R][MAXV];
+  uint4 raw[R2][VPL];
 #pragma unroll
-  for (int rr = 0; rr < R; ++rr) {
+  for (int rr = 0; rr < R2; ++rr) {
     const int row = row0 + rr < M ? row0 + rr : M - 1;   // clamp: rows past the end are loaded but not written
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + k * 32;
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = sub + k * lpr;
       raw[rr][k] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * ldx + vi * 8)) : make_uint4(0, 0, 0, 0);
     }
   }
-  float s[R], q[R];
+  float s[R2], q[R2];
 #pragma unroll
-  for (int rr = 0; rr < R; ++rr) {
+  for (int rr = 0; rr < R2; ++rr) {
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
+    for (int k = 0; k < VPL; ++k) {
       const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
       acc += ((a.x + a.y) + (b2.x + b2.y)) + ((c.x + c.y) + (d.x + d.y));   // padding vectors are zero
     }
     s[rr] = acc;
   }
+  for (int o = lpr >> 1; o > 0; o >>= 1)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
+    for (int rr = 0; rr < R2; ++rr) s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
-#pragma unroll
-  for (int rr = 0; rr < R; ++rr) {
+  for (int rr = 0; rr < R2; ++rr) {
     const float mean = s[rr] / (float)C;
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (lane + k * 32 < nvec) {
+    for (int k = 0; k < VPL; ++k) {
+      if (sub + k * lpr < nvec) {
         const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
         const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
 #pragma unroll
@@ -251,13 +255,12 @@ __global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld
     q[rr] = acc;
     s[rr] = mean;
   }
+  for (int o = lpr >> 1; o > 0; o >>= 1)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
+    for (int rr = 0; rr < R2; ++rr) q[rr] += __shfl_xor_sync(0xffffffffu, q[rr], o);
+  if (sub == 0) {
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) q[rr] += __shfl_xor_sync(0xffffffffu, q[rr], o);
-  if (lane == 0) {
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr)
+    for (int rr = 0; rr < R2; ++rr)
       if (row0 + rr < M) out[row0 + rr] = make_float2(s[rr], rsqrtf(q[rr] / (float)C + eps));
   }
 }
@@ -454,13 +457,16 @@ extern "C" int tair_row_stats(const void* x, int64_t ldx, float* out, int32_t M,
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   float2* op = reinterpret_cast<float2*>(out);
   const int nvec = C / 8;
-  // rows per warp: enough 16-byte loads in flight per lane (4-8) to cover the memory latency of a read-only kernel
-  auto grid_for = [&](int R) { const int rows_per_cta = warps * R; return (M + rows_per_cta - 1) / rows_per_cta; };
-  if (nvec <= 32) TAIR_LAUNCH((row_stats_kernel<1, 4>), grid_for(4), warps * 32, 0, st, xp, ldx, op, M, C, eps);
-  else if (nvec <= 64) TAIR_LAUNCH((row_stats_kernel<2, 4>), grid_for(4), warps * 32, 0, st, xp, ldx, op, M, C, eps);
-  else if (nvec <= 96) TAIR_LAUNCH((row_stats_kernel<3, 2>), grid_for(2), warps * 32, 0, st, xp, ldx, op, M, C, eps);
-  else if (nvec <= 160) TAIR_LAUNCH((row_stats_kernel<5, 1>), grid_for(1), warps * 32, 0, st, xp, ldx, op, M, C, eps);
-  else TAIR_LAUNCH((row_stats_kernel<8, 1>), grid_for(1), warps * 32, 0, st, xp, ldx, op, M, C, eps);
+  // lanes per row: the smallest power of two >= nvec / 5 (8 lanes for 320 channels, 16 for 640, 32 for 1280), at least 8
+  int lpr_log2 = 3;
+  while ((nvec + (1 << lpr_log2) - 1) / (1 << lpr_log2) > 5 && lpr_log2 < 5) ++lpr_log2;
+  const int vpl = (nvec + (1 << lpr_log2) - 1) / (1 << lpr_log2);
+  auto grid_for = [&](int R2) { const int rows_per_cta = warps * (32 >> lpr_log2) * R2; return (M + rows_per_cta - 1) / rows_per_cta; };
+  if (vpl <= 1) TAIR_LAUNCH((row_stats_kernel<1, 4>), grid_for(4), warps * 32, 0, st, xp, ldx, op, M, C, eps, lpr_log2);
+  else if (vpl <= 2) TAIR_LAUNCH((row_stats_kernel<2, 4>), grid_for(4), warps * 32, 0, st, xp, ldx, op, M, C, eps, lpr_log2);
+  else if (vpl <= 3) TAIR_LAUNCH((row_stats_kernel<3, 2>), grid_for(2), warps * 32, 0, st, xp, ldx, op, M, C, eps, lpr_log2);
+  else if (vpl <= 5) TAIR_LAUNCH((row_stats_kernel<5, 2>), grid_for(2), warps * 32, 0, st, xp, ldx, op, M, C, eps, lpr_log2);
+  else TAIR_LAUNCH((row_stats_kernel<8, 1>), grid_for(1), warps * 32, 0, st, xp, ldx, op, M, C, eps, lpr_log2);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("row_stats_kernel");
 }
