@@ -292,7 +292,8 @@ def main():
     ap.add_argument("--impl", default="tair", choices=["tair", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip full_step / e2e_pixels / gpu_eager_baseline")
+    ap.add_argument("--no-extras", action="store_true", help="skip full_step / e2e_pixels / cfg_sweep / gpu_eager_baseline")
+    ap.add_argument("--no-cfg-sweep", action="store_true", help="skip the classifier-free-guidance batch sweep (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -510,6 +511,31 @@ def main():
                               "collective": "none (1 rank)" if world == 1 else "1 x all_gather_into_tensor of decoded tiles + blend, inside the timed region",
                               "h2d_bytes_per_image": int(lq.nbytes), "d2h_bytes_per_image": int(img.numel() * 4),
                               "timed_images": KX, "image_crc32": f"{crc:08x}"}
+
+    if extras and not args.no_cfg_sweep:
+        # ---- configs[4], reduced to what one bench run can afford: classifier-free guidance (cond / uncond stacked as
+        # batch 2, scale 4.0, SURVEY §8a hazard 6) at several tiles-per-GPU batch sizes, one 50-step denoise each.  The
+        # full 3840x2160 image is 700 tiles; tools/config4_sweep.py runs it (and batch 64) outside the bench budget. ----
+        sweep = {}
+        un_txt = torch.randn((1, 77, 1024), device=dev, generator=g)
+        for bsz in (1, 4, 16, 32):
+            xs = torch.randn((bsz, 4, 64, 64), device=dev, generator=g)
+            ci = torch.randn((bsz, 4, 64, 64), device=dev, generator=g)
+            ct = torch.randn((bsz, 77, 1024), device=dev, generator=g)
+            un = dict(c_txt=un_txt.expand(bsz, -1, -1).contiguous(), c_img=ci)
+
+            def cfg_denoise():
+                flush.fill_(1)
+                z3, _ = sampler.sample(model, dev, SAMPLER_STEPS, (bsz, 4, 64, 64), dict(c_txt=ct, c_img=ci), un, 4.0, x_T=xs,
+                                       progress=False, use_cuda_graph=use_graph)
+                return z3
+            cfg_denoise()
+            ms_c, z3 = timed(cfg_denoise, 1)
+            assert torch.isfinite(z3).all()
+            sweep[str(bsz)] = {"patches_per_s": bsz * world / (ms_c * 1e-3), "ms_per_denoise_step": ms_c / SAMPLER_STEPS}
+        line["cfg_sweep"] = {"workload": "configs[4] (reduced): CFG scale 4.0 with cond/uncond stacked as batch 2 per tile, tiles-per-GPU "
+                                         "batch sweep, 50-step sampler, ControlNet + UNet + fused CFG update; one timed denoise per batch",
+                             "tiles_per_gpu": sweep, "unit": UNIT}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         usd = {k: v.detach().float().cpu() for k, v in model.unet.state_dict().items()}

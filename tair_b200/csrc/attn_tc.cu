@@ -56,6 +56,34 @@ struct AttnParams {
   int64_t o_outer, o_inner, o_tok;  // output row = outer*o_outer + inner*o_inner + token*o_tok
 };
 
+
+// P = exp2(S c - m) for one 128-wide S row held in registers -> packed bf16 pairs + four partial row sums.  Two
+// straight-line instantiations: the unmasked one (every block but the last / the causal diagonal / packed groups) carries
+// no per-element compare + select.  (Measured and rejected in round 2, tools/attn_probe.py + tools/probes/mufu_probe.cu:
+// forcing a FFMA / MUFU interleave with volatile asm — ptxas reschedules anyway, no change; packing to bf16 with integer
+// rounding + PRMT instead of F2FP — 473 vs 456 us; two query tiles per CTA whose softmax warps hand the MUFU to each other
+// through named barriers — 482 vs 456 us: one warp alone sustains one exponential per 9.4 cycles, two overlapping 8.3.)
+template <bool MASKED>
+__device__ __forceinline__ void softmax_exp_row(uint32_t (&sv)[AT_BN], float c, float m_run, int klo, int kvalid,
+                                                uint32_t (&pk)[AT_BN / 2], float& ls0, float& ls1, float& ls2, float& ls3) {
+#pragma unroll
+  for (int i = 0; i < AT_BN; i += 4) {
+    float e0 = ex2_approx(fmaf(__uint_as_float(sv[i + 0]), c, -m_run));
+    float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -m_run));
+    float e2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), c, -m_run));
+    float e3 = ex2_approx(fmaf(__uint_as_float(sv[i + 3]), c, -m_run));
+    if (MASKED) {
+      if (i + 0 >= kvalid || i + 0 < klo) e0 = 0.f;
+      if (i + 1 >= kvalid || i + 1 < klo) e1 = 0.f;
+      if (i + 2 >= kvalid || i + 2 < klo) e2 = 0.f;
+      if (i + 3 >= kvalid || i + 3 < klo) e3 = 0.f;
+    }
+    ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
+    pk[(i >> 1) + 0] = pack_bf16(e0, e1);
+    pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+  }
+}
+
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -262,33 +290,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // per-element compare+select — they were 2 of 7 instructions per element when the mask was predicated in.
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
       uint32_t pk[AT_BN / 2];
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < AT_BN; i += 4) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sv[i + 0]), c, -m_run));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -m_run));
-          const float e2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), c, -m_run));
-          const float e3 = ex2_approx(fmaf(__uint_as_float(sv[i + 3]), c, -m_run));
-          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
-          pk[(i >> 1) + 0] = pack_bf16(e0, e1);
-          pk[(i >> 1) + 1] = pack_bf16(e2, e3);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < AT_BN; i += 4) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(sv[i + 0]), c, -m_run));
-          float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -m_run));
-          float e2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), c, -m_run));
-          float e3 = ex2_approx(fmaf(__uint_as_float(sv[i + 3]), c, -m_run));
-          if (i + 0 >= kvalid || i + 0 < klo) e0 = 0.f;
-          if (i + 1 >= kvalid || i + 1 < klo) e1 = 0.f;
-          if (i + 2 >= kvalid || i + 2 < klo) e2 = 0.f;
-          if (i + 3 >= kvalid || i + 3 < klo) e3 = 0.f;
-          ls0 += e0; ls1 += e1; ls2 += e2; ls3 += e3;
-          pk[(i >> 1) + 0] = pack_bf16(e0, e1);
-          pk[(i >> 1) + 1] = pack_bf16(e2, e3);
-        }
-      }
+      if (full) softmax_exp_row<false>(sv, c, m_run, klo, kvalid, pk, ls0, ls1, ls2, ls3);
+      else softmax_exp_row<true>(sv, c, m_run, klo, kvalid, pk, ls0, ls1, ls2, ls3);
       if (j > 0) {                // P V(j-1) must have retired before O is rescaled or P is overwritten
         mbar_wait(p_free, (j - 1) & 1);
         tc_fence_after();
@@ -589,6 +592,7 @@ attn_kvs_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_dealloc(tmem, AT_TMEM_COLS);
   }
 }
+
 
 // 4-D view (column, token, inner sequence index, outer sequence index) of a row-major [rows, ld] bf16 matrix
 int make_map(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int64_t n_inner, int64_t n_outer,
