@@ -23,6 +23,7 @@ roofline   : dominant kernel family (3x3 implicit-GEMM conv, 47% of the FLOPs) t
 cpu_baseline      : the reference's CPU path on the host cores (the real reference modules when the reference tree is
                     importable — $TAIR_REF, /root/reference, baseline/_ref — else the oracle port), bounded sample.
 gpu_eager_baseline: the oracle port on cuda in fp32 with TF32 off ("the reference PyTorch path" on the same box), B=16.
+cfg_sweep  : configs[4] reduced — classifier-free guidance (cond/uncond stacked, scale 4.0) at 1 / 4 / 16 / 32 tiles per GPU.
 --impl reference  : the CPU path as its own arm, all host threads, same metric/config, extrapolated from a bounded sample.
 """
 from __future__ import annotations
@@ -408,8 +409,9 @@ def main():
                 "achieved": conv_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
                 "frac": conv_tflops / pk["tc_sustained"],
                 # ncu dram__bytes_read+write of ONE launch of the most frequent conv (B=16, 64x64, 320->320;
-                # profiles/round1_summary.md): 45.7 MB against 42+42 MB algorithmic in+out — the output stays in L2
-                "traffic": 45.7e6, "traffic_unit": "B per launch (64x64 320->320 conv, ncu --set full)",
+                # profiles/round2_ncu_full_step_kernels.csv, gemm_tc_kernel<160>, 119 us): 43.9 MB read + 5.4 MB written
+                # against 42 + 42 MB algorithmic in + out — the output stays in the 126 MB L2 for its consumer
+                "traffic": 49.3e6, "traffic_unit": "B per launch (64x64 320->320 conv, ncu --set full, round 2)",
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_denoise_step": n_conv, "avg_launch_ms": conv["ms"] / n_conv,
                 "flop_per_launch_avg": conv["work"] / n_conv}
@@ -486,7 +488,7 @@ def main():
                              "value": BATCH * world / (ms_full * 1e-3), "unit": UNIT, "ms_per_denoise": ms_full,
                              "ms_per_denoise_step": ms_full / SAMPLER_STEPS, "timed_denoises": KX,
                              "detections_last_step_tile0": len(res2[-1]["pred_texts"]),
-                             "gpu_launches_per_denoise": int(ops.launch_count()),
+                             "gpu_launches_outside_the_step_graph_per_denoise": int(ops.launch_count()),
                              "tokenizer": "hash stand-in (CLIP merge table not shipped)"}
 
         # ---- configs[3]: pixels to pixels, 512x512 LQ -> 25 tiles sharded over the ranks -> all-gather -> blend ----
