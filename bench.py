@@ -75,7 +75,7 @@ def hash_tokenizer(texts):
     import torch
     out = torch.zeros((len(texts), 77), dtype=torch.long)
     for i, s in enumerate(texts):
-        ids = [49406] + [zlib.crc32(w.encode()) % 49000 for w in s.split()][:75] + [49407]
+        ids = [49406] + [zlib.crc32(w.encode()) % 49000 for w in s.split(None, 76)[:75]] + [49407]
         out[i, :len(ids)] = torch.tensor(ids)
     return out
 

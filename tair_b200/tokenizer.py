@@ -105,10 +105,14 @@ class BPETokenizer:
         text = html.unescape(html.unescape(text)).strip()
         return regex.sub(r"\s+", " ", text).strip().lower()
 
-    def encode(self, text: str) -> List[int]:
+    def encode(self, text: str, max_tokens: int = 0) -> List[int]:
+        """``max_tokens`` > 0 stops once that many tokens exist (pre-tokens are independent, so the prefix is exact): the
+        sampler's prompts list up to 100 recognised strings per tile per step and only the first 75 tokens survive."""
         out: List[int] = []
-        for tok in self._split.findall(self._clean(text)):
-            out.extend(self._merge_word("".join(self.byte_sym[b] for b in tok.encode("utf-8"))))
+        for m in self._split.finditer(self._clean(text)):
+            out.extend(self._merge_word("".join(self.byte_sym[b] for b in m.group(0).encode("utf-8"))))
+            if max_tokens and len(out) >= max_tokens:
+                break
         return out
 
     def decode(self, ids: Iterable[int]) -> str:
@@ -120,7 +124,7 @@ class BPETokenizer:
             texts = [texts]
         out = torch.zeros((len(texts), context_length), dtype=torch.long)
         for i, t in enumerate(texts):
-            ids = [self.sot_id] + self.encode(t) + [self.eot_id]
+            ids = [self.sot_id] + self.encode(t, context_length) + [self.eot_id]
             if len(ids) > context_length:
                 ids = ids[:context_length]
                 ids[-1] = self.eot_id
