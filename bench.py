@@ -492,16 +492,24 @@ def main():
                              "tokenizer": "hash stand-in (CLIP merge table not shipped)"}
 
         # ---- configs[3]: pixels to pixels, 512x512 LQ -> 25 tiles sharded over the ranks -> all-gather -> blend ----
-        lq = np.random.default_rng(0).integers(0, 256, (512, 512, 3), dtype=np.uint8)
+        # a DIFFERENT image per call: restoring one image over and over would find every prompt of the previous pass in
+        # the text encoder's prompt memo and skip the OpenCLIP re-encode that a real stream of images pays
+        lqs = [np.random.default_rng(i).integers(0, 256, (512, 512, 3), dtype=np.uint8) for i in range(KX + 1)]
+        lq = lqs[0]
         n_tiles = 25
+        calls = [0]
 
         def restore():
             flush.fill_(1)
+            lq = lqs[calls[0] % len(lqs)]
+            calls[0] += 1
             out = pipeline.restore_image(lq, model, sampler, steps=SAMPLER_STEPS, tile_batch=BATCH, ts_model=det, cfg=vcfg,
                                          cleaner=lambda x: cleaner(x).clamp(0, 1), use_cuda_graph=use_graph)
             return out.cpu()
-        restore()       # graph captures for this rank's tile-batch sizes
+        restore()       # graph captures for this rank's tile-batch sizes (image 0; the timed calls restore images 1..KX)
+        req0, enc0 = model.clip.prompts_requested, model.clip.prompts_encoded
         ms_pix, img = timed(restore, KX)
+        req1, enc1 = model.clip.prompts_requested, model.clip.prompts_encoded
         assert tuple(img.shape) == (1, 3, 2048, 2048) and torch.isfinite(img).all()
         crc = zlib.crc32(img.numpy().tobytes())
         line["e2e_pixels"] = {"workload": "configs[3]: HOST uint8 512x512 LQ image -> 25 overlapping 128^2 tiles -> GPU crop + "
@@ -512,7 +520,9 @@ def main():
                               "tiles_per_rank_max": (n_tiles + world - 1) // world, "scaling": "strong",
                               "collective": "none (1 rank)" if world == 1 else "1 x all_gather_into_tensor of decoded tiles + blend, inside the timed region",
                               "h2d_bytes_per_image": int(lq.nbytes), "d2h_bytes_per_image": int(img.numel() * 4),
-                              "timed_images": KX, "image_crc32": f"{crc:08x}"}
+                              "timed_images": KX, "images": "a different synthetic image per call",
+                              "prompts_per_image_this_rank": {"requested": (req1 - req0) // KX, "encoded_by_openclip": (enc1 - enc0) // KX},
+                              "image_crc32": f"{crc:08x}"}
 
     if extras and not args.no_cfg_sweep:
         # ---- configs[4], reduced to what one bench run can afford: classifier-free guidance (cond / uncond stacked as

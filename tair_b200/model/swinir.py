@@ -223,14 +223,14 @@ class SwinIR(nn.Module):
         entry = self._graphs.get(key)
         if entry is None:
             buf = x.float().clone()
-            side = torch.cuda.Stream()
+            side = self._side = getattr(self, "_side", None) or torch.cuda.Stream()   # one stream for warm-up AND capture
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):   # warm-up outside capture: packing, index maps, tile tuning, allocator
+            with torch.cuda.stream(side):   # warm-up outside capture: packing, index maps, tile tuning, allocator, workspaces
                 for _ in range(2):
                     self._forward(buf)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):
                 out = self._forward(buf)
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))

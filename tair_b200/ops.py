@@ -157,6 +157,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rowgroup
 
 
 _sk_ws: dict = {}
+# A workspace that is outgrown is RETIRED, never freed: a captured CUDA graph may hold its address (graphs are captured on
+# the warm-up stream, so the workspaces of that stream are shared by every graph captured there).
+_retired_ws: list = []
 
 
 def _splitk_workspace(device, need: int) -> torch.Tensor:
@@ -165,6 +168,8 @@ def _splitk_workspace(device, need: int) -> torch.Tensor:
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _sk_ws.get(key)
     if ws is None or ws.numel() < need:
+        if ws is not None:
+            _retired_ws.append(ws)
         ws = torch.empty(max(need, 16 << 20), device=device, dtype=torch.uint8)
         _sk_ws[key] = ws
     return ws
@@ -247,6 +252,8 @@ def _gn_workspace(device, B: int, groups: int) -> torch.Tensor:
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _gn_ws.get(key)
     if ws is None or ws.numel() < need:
+        if ws is not None:
+            _retired_ws.append(ws)
         ws = torch.empty(max(need, 1 << 20), device=device, dtype=torch.uint8)
         _gn_ws[key] = ws
     return ws

@@ -334,7 +334,9 @@ class _StepGraph:
                 self._step()
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # capture on the SAME stream the warm-up ran on: the per-stream GroupNorm / split-K workspaces of ``ops`` were
+        # allocated there outside the capture, so no workspace ends up inside one graph's private memory pool
+        with torch.cuda.graph(g, stream=side):
             out, feats, dense = self._step()
         self.graph = (g, out, feats, dense)
 

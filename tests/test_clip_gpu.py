@@ -83,3 +83,45 @@ def test_clip_last_layer_and_tokenizer_hook(clip):
     m.attach_tokenizer(lambda texts: tokens[:len(texts)].cpu())
     assert torch.equal(m.encode(["x", "y"]), m(tokens[:2]))
     m.attach_tokenizer(None)
+
+
+def test_clip_prompt_memo_rows_eviction_and_weight_change(clip):
+    """encode() memoises prompt embeddings in ONE preallocated row buffer: repeated and re-ordered prompts come back
+    identical, the least recently used rows are evicted first (never a prompt of the current call), a call with more
+    distinct prompts than rows grows the buffer, and changing a weight in place drops every memoised row."""
+    import zlib
+    from tair_b200.model.clip import FrozenOpenCLIPEmbedder
+    m, _ = clip
+    e = FrozenOpenCLIPEmbedder(1024, VISION_CFG, TEXT_CFG, layer="penultimate").cuda().eval()
+    e.load_state_dict(m.state_dict())
+    e.cache_size = 6
+
+    def tok(texts):
+        out = torch.zeros((len(texts), 77), dtype=torch.long)
+        for i, t in enumerate(texts):
+            g = torch.Generator().manual_seed(zlib.crc32(t.encode()))
+            out[i, :8] = torch.randint(1, 49000, (8,), generator=g)
+        return out
+    calls = []
+    e.attach_tokenizer(lambda texts: (calls.append(list(texts)), tok(texts))[1])
+    direct = lambda texts: e(tok(texts).cuda())                         # noqa: E731
+    a = e.encode(["p0", "p1", "p2", "p1"])
+    assert calls == [["p0", "p1", "p2"]] and a.shape == (4, 77, 1024)
+    assert torch.equal(a, direct(["p0", "p1", "p2", "p1"]))
+    ptr = e._rows.data_ptr()
+    b = e.encode(["p2", "p0", "p3"])                                    # two hits, one new
+    assert calls[-1] == ["p3"] and torch.equal(b, direct(["p2", "p0", "p3"]))
+    e.encode(["p4", "p5", "p6"])                                        # 7 prompts, 6 rows: p1 (least recent) leaves
+    assert "p1" not in e._cache and len(e._cache) == 6 and e._rows.data_ptr() == ptr
+    c = e.encode(["p0", "p1"])                                          # p0 still memoised; p1 re-encoded, p2 leaves
+    assert calls[-1] == ["p1"] and "p2" not in e._cache
+    assert torch.equal(c, direct(["p0", "p1"]))
+    many = [f"q{i}" for i in range(9)]                                  # more distinct prompts than rows: buffer grows
+    d = e.encode(many)
+    assert e._rows.shape[0] == 9 and torch.equal(d, direct(many))
+    n_calls = len(calls)
+    assert torch.equal(e.encode(many[::-1]), d.flip(0)) and len(calls) == n_calls
+    with torch.no_grad():
+        e.model.ln_final.weight.mul_(2.0)                               # in-place weight change: memo must be dropped
+    d2 = e.encode(many)
+    assert len(calls) == n_calls + 1 and not torch.equal(d2, d) and torch.equal(d2, direct(many))
