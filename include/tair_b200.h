@@ -68,13 +68,16 @@ typedef struct tair_epilogue {
   const float* bias;       /* [N] fp32 or NULL                                         */
   const void* residual;    /* [M, ldr] bf16 added after the activation, or NULL        */
   int64_t ldr;
-  const float* rowgroup;   /* fp32 [G, ldg] added before act, or NULL.  rows_per_group > 0: row m uses
+  const void* rowgroup;    /* fp32 (bf16 when rowgroup_bf16 != 0) [G, ldg] added before act, or NULL.  rows_per_group > 0: row m uses
                               rowgroup[m / rows_per_group] (timestep-embedding add: one row per image);
                               rows_per_group < 0: periodic, row m uses rowgroup[m % -rows_per_group]
                               (positional-embedding projections shared by every image)     */
   int64_t ldg;
   int32_t rows_per_group;
-  int32_t reserved;
+  int32_t rowgroup_bf16;   /* 0: fp32 rows.  1: bf16 rows, prefetched like the residual (half the L2 traffic of the fp32
+                              form; TESTR's per-query positional projections).  Needs a 16-byte aligned bf16 output,
+                              N % 32 == 0, rows 16-byte aligned (ldg % 8 == 0), act == NONE, no residual, no folded
+                              LayerNorm; TAIR_ERR_INVALID otherwise.                       */
   void* workspace;         /* optional scratch (16-byte aligned, private to the stream) or NULL.  When given and large
                               enough (3 * M * N * 4 bytes), tair_conv3x3_bf16 computes layers whose OUTPUT image is at
                               most 8x8 with K >= 4096 as a 3-way split-K: fp32 partial tiles in the workspace, then

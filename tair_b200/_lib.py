@@ -35,7 +35,7 @@ class Epilogue(C.Structure):
         ("rowgroup", C.c_void_p),
         ("ldg", C.c_int64),
         ("rows_per_group", C.c_int32),
-        ("reserved", C.c_int32),
+        ("rowgroup_bf16", C.c_int32),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
         ("ln_row_stats", C.c_void_p),

@@ -98,6 +98,6 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }  // namespace tair
 
 extern "C" const char* tair_last_error(void) { return tair::g_err; }
-extern "C" int tair_abi_version(void) { return 3; }  // 3: sampler_update cfg_scale_dev, GroupNorm statistics from the producer, LayerNorm folded into GEMM
+extern "C" int tair_abi_version(void) { return 4; }  // 4: tair_epilogue.rowgroup_bf16 (was `reserved`), rowgroup is const void*
 extern "C" int64_t tair_launch_count(void) { return tair::g_launch_count.load(); }
 extern "C" void tair_launch_count_reset(void) { tair::g_launch_count.store(0); }

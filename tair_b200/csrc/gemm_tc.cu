@@ -50,6 +50,10 @@ struct GemmParams {
   int Ho, Wo, stride, pad;
   int vec_out, vec_res, vec_rg, vec_bias;
   int tma_store;  // bf16 output eligible for the TMA-store epilogue
+  int stages;     // depth of the operand ring and number of epilogue staging buffers per warp (1 or 2): chosen per launch
+  int stg_bufs;   // (pick_staging) - a second staging buffer costs ring stages, which only short K loops can spare
+  int epi_mode;   // TMA-store epilogue variant: 0 lean (bias / activation only), 1 lean + one prefetched bf16 row-add
+                  // stream (residual, or bf16 row-group rows), 2 generic (fp32 row groups, folded LayerNorm, GEGLU, tails)
   int splits;      // split-K: each tile is computed by `splits` CTAs over kb_split k-blocks each; fp32 partials go to
   int kb_split;    // rows [split*M, split*M + M) of the (workspace) output, a second kernel reduces + applies the epilogue
   int dbg;  // bring-up probes (TAIR_GEMM_DEBUG): 1 skip global stores, 2 skip the epilogue body, 4 / 8 load B / A only for the first tile
@@ -60,10 +64,16 @@ template <int BN>
 struct Cfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int FIT = (int)((232448u - 1280u - STG_BYTES) / STAGE_BYTES);  // 227 KB opt-in limit per CTA
-  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  // ring depth with `bufs` staging buffers per epilogue warp inside the 227 KB opt-in limit per CTA
+  static constexpr int stages_for(int bufs) {
+    const int fit = (int)((232448u - 1280u - (uint32_t)bufs * STG_BYTES) / STAGE_BYTES);
+    return fit > 8 ? 8 : fit;
+  }
+  static constexpr uint32_t smem_for(int bufs) {
+    return (uint32_t)stages_for(bufs) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + (uint32_t)bufs * STG_BYTES;
+  }
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
+  static constexpr uint32_t SMEM_MAX = smem_for(1) > smem_for(2) ? smem_for(1) : smem_for(2);
 };
 
 template <int ACT>
@@ -135,7 +145,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
   const tair_epilogue& e = p.epi;
       const float* rg = nullptr;
       if (e.rowgroup != nullptr && row_ok)
-        rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
+        rg = reinterpret_cast<const float*>(e.rowgroup) + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
       // folded LayerNorm: acc' = rstd * (acc - mean * colsum[n]) = acc * ln_r + ln_c * colsum[n]
       float ln_r = 1.f, ln_c = 0.f;
       const float* lcs = e.ln_row_stats != nullptr ? e.ln_col_sum : nullptr;
@@ -220,8 +230,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m, int tn
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC64,
                                                   const CUtensorMap* tmC32, int m0q, int tn, int half, int lane,
-                                                  uint32_t taddr, uint8_t* stg, uint32_t tempty_bar_addr,
-                                                  bool remote_arrive, uint32_t tfull_bar_addr, uint32_t tfull_phase) {
+                                                  uint32_t taddr, uint8_t* stg0, uint32_t tempty_bar_addr,
+                                                  bool remote_arrive, uint32_t tfull_bar_addr, uint32_t tfull_phase,
+                                                  uint32_t& stg_sel) {
   const tair_epilogue& e = p.epi;
   constexpr bool GEGLU = (ACT == TAIR_ACT_GEGLU);
   constexpr int NT = GEGLU ? BN / 2 : BN;      // output columns produced by this tile
@@ -232,7 +243,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   const bool row_ok = m < p.M;
   const float* rg = nullptr;
   if (!GEGLU && e.rowgroup != nullptr && row_ok)
-    rg = e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
+    rg = reinterpret_cast<const float*>(e.rowgroup) + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
   const __nv_bfloat16* resp = (e.residual != nullptr && row_ok)
                                   ? reinterpret_cast<const __nv_bfloat16*>(e.residual) + (int64_t)m * e.ldr : nullptr;
   // folded LayerNorm (tair_epilogue.ln_row_stats): acc' = rstd * (acc - mean * colsum[n]) = acc * ln_r + ln_c * colsum[n]
@@ -243,7 +254,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     ln_r = st.y;
     ln_c = -st.x * st.y;
   }
-  const uint32_t stg_u32 = smem_u32(stg);
   const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
 
   auto release = [&]() {  // tempty lives in the leader CTA of a pair when remote_arrive is set
@@ -275,7 +285,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   for (int s = half; s < NSUB; s += 2) {
     const int c0 = s * 64;
     const int ncol = (NT - c0) < 64 ? (NT - c0) : 64;  // 64, or 32 for the tail of BN = 160
-    if (elect_one()) tma_store_wait_read<0>();         // previous store of this warp has left the staging buffer
+    uint8_t* stg = stg0 + stg_sel * STG_BYTES;         // this warp's staging buffer for this sub-tile (1 or 2 of them)
+    const uint32_t stg_u32 = smem_u32(stg);
+    if (elect_one()) {   // the store that last used this buffer has left it
+      if (p.stg_bufs == 2) tma_store_wait_read<1>();
+      else tma_store_wait_read<0>();
+    }
     __syncwarp();
 #pragma unroll 1
     for (int g = 0; g < ncol; g += 32) {
@@ -405,10 +420,213 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       if (last) release();
       if (!(p.dbg & 1)) {
         tma_store_2d(ncol == 64 ? tmC64 : tmC32, stg_u32, n_out0 + c0, m0q);
-        tma_store_commit();
       }
+      tma_store_commit();   // (an empty group under dbg & 1 keeps the wait_group accounting of two buffers right)
+    }
+    stg_sel ^= (uint32_t)(p.stg_bufs - 1);
+  }
+}
+
+// Lean variants of the TMA-store epilogue.  The generic function above executes ~110 instructions per 32-column group
+// even when it has nothing to add (register copies of the residual prefetch, predicated-off loads, 64-bit generic store
+// addressing, null checks: ncu source page of 151552x1024x256, profiles/round2_summary.md), and an epilogue warp is one
+// serial instruction stream: at K = 256 the drain of a tile then takes longer than its main loop.  Here every group is
+// tcgen05.ld -> bias -> activation -> (row add) -> pack -> 4 x st.shared.v4, and the row-add stream (the bf16 residual
+// row, or the bf16 row-group row of this output row) is prefetched a whole 64-column sub-tile ahead into registers that
+// are refilled in place (no copies).  Host guarantees (pick_epi_mode): N % 32 == 0, 16-byte aligned bias / add rows.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+template <int BN, int ACT, bool ROWADD>
+__device__ __forceinline__ void epilogue_tile_tma_lean(const GemmParams& p, const CUtensorMap* tmC64,
+                                                       const CUtensorMap* tmC32, int m0q, int tn, int half, int lane,
+                                                       uint32_t taddr, uint8_t* stg0, uint32_t tempty_bar_addr,
+                                                       bool remote_arrive, uint32_t tfull_bar_addr,
+                                                       uint32_t tfull_phase, uint32_t& stg_sel) {
+  const tair_epilogue& e = p.epi;
+  constexpr int NSUB = (BN + 63) / 64;
+  const int n_out0 = tn * BN;
+  const int m = m0q + lane;
+  const __nv_bfloat16* addp = nullptr;   // this row's bf16 add stream (ROWADD)
+  if constexpr (ROWADD) {
+    if (m < p.M) {
+      if (e.residual != nullptr)
+        addp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + (int64_t)m * e.ldr;
+      else
+        addp = reinterpret_cast<const __nv_bfloat16*>(e.rowgroup) +
+               (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
     }
   }
+  const float* bias = e.bias;
+  const uint32_t sw7 = lane & 7, sw3 = (lane >> 1) & 3;
+  auto release = [&]() {
+    if (remote_arrive) mbar_arrive_cluster(tempty_bar_addr);
+    else mbar_arrive(tempty_bar_addr);
+  };
+  // add rows of the sub-tile being drained: ra0 = its first 32 columns, ra1 = its second 32 columns.  Two named arrays
+  // and two lambdas on purpose: indexing one array through a pointer argument put it in local memory.
+  uint4 ra0[4] = {}, ra1[4] = {};
+  auto prefetch0 = [&](int n) {   // columns [n, n + 32) of this row, if they exist
+    if (addp != nullptr && n < p.N) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ra0[q] = __ldg(reinterpret_cast<const uint4*>(addp + n) + q);
+    }
+  };
+  auto prefetch1 = [&](int n) {
+    if (addp != nullptr && n < p.N) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ra1[q] = __ldg(reinterpret_cast<const uint4*>(addp + n) + q);
+    }
+  };
+  if constexpr (ROWADD) {
+    if (half < NSUB) {
+      prefetch0(n_out0 + half * 64);
+      if (BN - half * 64 > 32) prefetch1(n_out0 + half * 64 + 32);
+    }
+  }
+  mbar_wait(tfull_bar_addr, tfull_phase);
+  tc_fence_after();
+  if (half >= NSUB) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) release();
+    return;
+  }
+  // bias -> activation -> row add on one 32-column group held in r[] (in place)
+  auto finish = [&](uint32_t (&r)[32], int n, const uint4 (&ra)[4]) {
+    if (n >= p.N) return;                  // warp-uniform: whole 32-column groups are inside or outside N
+    if (bias != nullptr) {                 // the same address in every lane: broadcast loads, L1-resident after tile 0
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n) + q);
+        r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + t.x);
+        r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + t.y);
+        r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + t.z);
+        r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + t.w);
+      }
+    }
+    if constexpr (ACT != TAIR_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(apply_act<ACT>(__uint_as_float(r[j])));
+    }
+    if constexpr (ROWADD) {
+      if (addp != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 w = ra[q];
+          const float2 b0 = unpack_bf16(w.x), b1 = unpack_bf16(w.y), b2 = unpack_bf16(w.z), b3 = unpack_bf16(w.w);
+          r[q * 8 + 0] = __float_as_uint(__uint_as_float(r[q * 8 + 0]) + b0.x);
+          r[q * 8 + 1] = __float_as_uint(__uint_as_float(r[q * 8 + 1]) + b0.y);
+          r[q * 8 + 2] = __float_as_uint(__uint_as_float(r[q * 8 + 2]) + b1.x);
+          r[q * 8 + 3] = __float_as_uint(__uint_as_float(r[q * 8 + 3]) + b1.y);
+          r[q * 8 + 4] = __float_as_uint(__uint_as_float(r[q * 8 + 4]) + b2.x);
+          r[q * 8 + 5] = __float_as_uint(__uint_as_float(r[q * 8 + 5]) + b2.y);
+          r[q * 8 + 6] = __float_as_uint(__uint_as_float(r[q * 8 + 6]) + b3.x);
+          r[q * 8 + 7] = __float_as_uint(__uint_as_float(r[q * 8 + 7]) + b3.y);
+        }
+      }
+    }
+  };
+  auto stage = [&](const uint32_t (&r)[32], uint32_t stg_u32, int g, int ncol) {   // pack + swizzled 16-byte stores
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t dst = (ncol == 64) ? stg_u32 + lane * 128 + (((uint32_t)((g >> 3) + q) ^ sw7) << 4)
+                                        : stg_u32 + lane * 64 + (((uint32_t)q ^ sw3) << 4);
+      sts128(dst, pack_bf16(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1])),
+             pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
+             pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])),
+             pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
+    }
+  };
+  auto wait_buffer = [&]() {   // the store that last used the staging buffer about to be written has left it
+    if (elect_one()) {
+      if (p.stg_bufs == 2) tma_store_wait_read<1>();
+      else tma_store_wait_read<0>();
+    }
+  };
+  auto store = [&](uint32_t stg_u32, int n, bool wide, bool last) {
+    if (last) tc_fence_before();   // all TMEM reads of this tile by this warp are done
+    fence_async_smem();            // staging writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (elect_one()) {
+      if (last) release();
+      if (!(p.dbg & 1)) tma_store_2d(wide ? tmC64 : tmC32, stg_u32, n, m0q);
+      tma_store_commit();          // (an empty group under dbg & 1 keeps the two-buffer wait_group accounting right)
+    }
+    stg_sel ^= (uint32_t)(p.stg_bufs - 1);
+  };
+  constexpr int NFULL = BN / 64;             // full 64-column sub-tiles; BN = 96 / 160 / 224 end with a 32-column one
+  constexpr bool TAIL = (BN % 64) != 0;
+#pragma unroll 1
+  for (int s = half; s < NFULL; s += 2) {
+    const bool more = s + 2 < NSUB;
+    const int n = n_out0 + s * 64;
+    const uint32_t stg_u32 = smem_u32(stg0 + stg_sel * STG_BYTES);
+    // both halves of the sub-tile leave tensor memory together: one load latency per 64 columns instead of two
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(taddr + s * 64, r0);
+    tmem_ld_32x32(taddr + s * 64 + 32, r1);
+    wait_buffer();
+    tmem_ld_wait();
+    __syncwarp();
+    finish(r0, n, ra0);
+    if constexpr (ROWADD) {   // refill the registers just consumed with the same group of this warp's next sub-tile
+      if (more) prefetch0(n + 128);
+    }
+    stage(r0, stg_u32, 0, 64);
+    finish(r1, n + 32, ra1);
+    if constexpr (ROWADD) {
+      if (more && s * 64 + 128 + 32 < BN) prefetch1(n + 128 + 32);
+    }
+    stage(r1, stg_u32, 32, 64);
+    store(stg_u32, n, true, !more);
+  }
+  if constexpr (TAIL) {
+    if ((NFULL & 1) == half) {   // the 32-column tail belongs to the warp whose sub-tile parity it continues
+      const int n = n_out0 + NFULL * 64;
+      const uint32_t stg_u32 = smem_u32(stg0 + stg_sel * STG_BYTES);
+      uint32_t r0[32];
+      tmem_ld_32x32(taddr + NFULL * 64, r0);
+      wait_buffer();
+      tmem_ld_wait();
+      __syncwarp();
+      finish(r0, n, ra0);
+      stage(r0, stg_u32, 0, 32);
+      store(stg_u32, n, false, true);
+    }
+  }
+}
+
+// activation x variant dispatch of the TMA-store epilogue (warp-uniform switch, one call per tile)
+template <int BN>
+__device__ __forceinline__ void epilogue_dispatch_tma(const GemmParams& p, const CUtensorMap* tmC64,
+                                                      const CUtensorMap* tmC32, int m0q, int tn, int half, int lane,
+                                                      uint32_t taddr, uint8_t* stg, uint32_t tempty_bar_addr,
+                                                      bool remote_arrive, uint32_t tfull_bar_addr,
+                                                      uint32_t tfull_phase, uint32_t& stg_sel) {
+#define TAIR_EPI_ARGS p, tmC64, tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar_addr, remote_arrive, tfull_bar_addr, tfull_phase, stg_sel
+  const int act = p.epi.act;
+  if (p.epi_mode == 0) {
+    switch (act) {
+      case TAIR_ACT_GELU: epilogue_tile_tma_lean<BN, TAIR_ACT_GELU, false>(TAIR_EPI_ARGS); return;
+      case TAIR_ACT_SILU: epilogue_tile_tma_lean<BN, TAIR_ACT_SILU, false>(TAIR_EPI_ARGS); return;
+      case TAIR_ACT_RELU: epilogue_tile_tma_lean<BN, TAIR_ACT_RELU, false>(TAIR_EPI_ARGS); return;
+      default: epilogue_tile_tma_lean<BN, TAIR_ACT_NONE, false>(TAIR_EPI_ARGS); return;
+    }
+  }
+  if (p.epi_mode == 1) {   // activation NONE only (pick_epi_mode)
+    epilogue_tile_tma_lean<BN, TAIR_ACT_NONE, true>(TAIR_EPI_ARGS);
+    return;
+  }
+  switch (act) {
+    case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(TAIR_EPI_ARGS); break;
+    case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(TAIR_EPI_ARGS); break;
+    case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(TAIR_EPI_ARGS); break;
+    case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(TAIR_EPI_ARGS); break;
+    default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(TAIR_EPI_ARGS); break;
+  }
+#undef TAIR_EPI_ARGS
 }
 
 template <int BN>
@@ -417,11 +635,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmC64, const __grid_constant__ CUtensorMap tmC32,
                const GemmParams p) {
   using C = Cfg<BN>;
-  constexpr int STAGES = C::STAGES;
+  const int STAGES = p.stages;   // runtime: see GemmParams.stages / stg_bufs
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + p.stg_bufs * STG_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const uint32_t smem_base = smem_u32(smem);
@@ -558,7 +776,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = ew & 3;   // TMEM lane quadrant (== warp % 4, the only lanes this warp may read)
     const int half = ew >> 2;  // which alternate 64-column sub-tiles this warp drains
     const tair_epilogue& e = p.epi;
-    uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
+    uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;   // buffer b of this warp: + b * STG_BYTES
+    uint32_t stg_sel = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
@@ -575,13 +794,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       } else if (p.tma_store) {
-        switch (e.act) {
-          case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
-          case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
-          case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
-          case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
-          default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase); break;
-        }
+        epilogue_dispatch_tma<BN>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_bar(acc), false, tfull_bar(acc), acc_phase, stg_sel);
       } else {
         // fp32 / unaligned outputs (small heads): direct thread-per-row stores by the first four epilogue warps
         const bool row_ok = m0q + lane < p.M;
@@ -622,10 +835,15 @@ template <int BN>
 struct Cfg2 {
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int FIT = (int)((232448u - 1280u - STG_BYTES) / STAGE_BYTES);
-  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int stages_for(int bufs) {
+    const int fit = (int)((232448u - 1280u - (uint32_t)bufs * STG_BYTES) / STAGE_BYTES);
+    return fit > 8 ? 8 : fit;
+  }
+  static constexpr uint32_t smem_for(int bufs) {
+    return (uint32_t)stages_for(bufs) * STAGE_BYTES + 1024 + 256 + (uint32_t)bufs * STG_BYTES;
+  }
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + STG_BYTES;
+  static constexpr uint32_t SMEM_MAX = smem_for(1) > smem_for(2) ? smem_for(1) : smem_for(2);
 };
 
 template <int BN>
@@ -634,11 +852,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmC64, const __grid_constant__ CUtensorMap tmC32,
                 const GemmParams p) {
   using C = Cfg2<BN>;
-  constexpr int STAGES = C::STAGES;
+  const int STAGES = p.stages;   // runtime: see GemmParams.stages / stg_bufs
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
+  uint8_t* stg_base = smem + STAGES * C::STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + p.stg_bufs * STG_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const uint32_t smem_base = smem_u32(smem);
@@ -771,7 +989,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = ew & 3;
     const int half = ew >> 2;
     const tair_epilogue& e = p.epi;
-    uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;
+    uint8_t* stg = stg_base + ew * STG_BYTES_PER_WARP;   // buffer b of this warp: + b * STG_BYTES
+    uint32_t stg_sel = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -788,13 +1007,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(tempty_leader); else mbar_arrive_cluster(tempty_leader); }
       } else
-      switch (e.act) {
-        case TAIR_ACT_GEGLU: epilogue_tile_tma<BN, TAIR_ACT_GEGLU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
-        case TAIR_ACT_GELU: epilogue_tile_tma<BN, TAIR_ACT_GELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
-        case TAIR_ACT_SILU: epilogue_tile_tma<BN, TAIR_ACT_SILU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
-        case TAIR_ACT_RELU: epilogue_tile_tma<BN, TAIR_ACT_RELU>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
-        default: epilogue_tile_tma<BN, TAIR_ACT_NONE>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase); break;
-      }
+        epilogue_dispatch_tma<BN>(p, &tmC64, &tmC32, m0q, tn, half, lane, taddr, stg, tempty_leader, !leader, tfull_bar(acc), acc_phase, stg_sel);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -810,14 +1023,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// One or two epilogue staging buffers per warp.  With one, a warp cannot write sub-tile i+1 before the bulk store of
+// sub-tile i has read the buffer (ncu source page of 151552x1024x256: the largest single stall of the epilogue warps).
+// Measured, though, the second buffer (which costs 32 KB = one stage of the operand ring) changes nothing: K = 256 GEMMs
+// 39.4 / 36.6 / 28.1 / 91.0 us with two buffers vs 39.3 / 35.9 / 26.7 / 89.5 with one, B=16 step 22.75 ms both ways
+// (profiles/round2_summary.md) - these GEMMs are bound by HBM reads competing with their own output writes, not by
+// the drain.  Default is therefore one buffer; TAIR_EPI_STG=2 selects two for K <= 512 GEMMs (probe).
+int pick_staging(const GemmParams& p) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* v = getenv("TAIR_EPI_STG");
+    forced = v ? atoi(v) : 1;
+  }
+  if (forced == 2) return (p.tma_store && !p.conv && p.num_kb <= 8) ? 2 : 1;
+  return 1;
+}
+
 template <int BN>
 int launch_bn2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
                const GemmParams& p, cudaStream_t st) {
-  TAIR_SMEM_OPTIN(gemm_tc2_kernel<BN>, Cfg2<BN>::SMEM_BYTES);
+  TAIR_SMEM_OPTIN(gemm_tc2_kernel<BN>, Cfg2<BN>::SMEM_MAX);
+  GemmParams q = p;
+  q.stg_bufs = pick_staging(p);
+  q.stages = Cfg2<BN>::stages_for(q.stg_bufs);
   const int tiles2 = ((p.tiles_m + 1) / 2) * p.tiles_n;
   int pairs = num_sms() / 2;
   if (tiles2 < pairs) pairs = tiles2;
-  TAIR_LAUNCH((gemm_tc2_kernel<BN>), 2 * pairs, GEMM_THREADS, Cfg2<BN>::SMEM_BYTES, st, tmA, tmB, tmC64, tmC32, p);
+  TAIR_LAUNCH((gemm_tc2_kernel<BN>), 2 * pairs, GEMM_THREADS, Cfg2<BN>::smem_for(q.stg_bufs), st, tmA, tmB, tmC64, tmC32, q);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("gemm_tc2_kernel");
 }
@@ -825,10 +1057,13 @@ int launch_bn2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
 template <int BN>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC64, const CUtensorMap& tmC32,
               const GemmParams& p, cudaStream_t st) {
-  TAIR_SMEM_OPTIN(gemm_tc_kernel<BN>, Cfg<BN>::SMEM_BYTES);
+  TAIR_SMEM_OPTIN(gemm_tc_kernel<BN>, Cfg<BN>::SMEM_MAX);
+  GemmParams q = p;
+  q.stg_bufs = pick_staging(p);
+  q.stages = Cfg<BN>::stages_for(q.stg_bufs);
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  TAIR_LAUNCH((gemm_tc_kernel<BN>), grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmB, tmC64, tmC32, p);
+  TAIR_LAUNCH((gemm_tc_kernel<BN>), grid, GEMM_THREADS, Cfg<BN>::smem_for(q.stg_bufs), st, tmA, tmB, tmC64, tmC32, q);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return check_launch("gemm_tc_kernel");
 }
@@ -881,6 +1116,24 @@ bool use_2cta(const GemmParams& p, int bn) {
   return bn == 256 && p.num_kb >= 16 && tiles2 >= 2 * (num_sms() / 2);
 }
 
+// Which TMA-store epilogue drains the tiles (GemmParams.epi_mode).  TAIR_EPI_LEAN=0 forces the generic one (A/B probe).
+int pick_epi_mode(const GemmParams& p) {
+  static int lean = -1;
+  if (lean < 0) {
+    const char* v = getenv("TAIR_EPI_LEAN");
+    lean = v ? atoi(v) : 1;
+  }
+  const tair_epilogue& e = p.epi;
+  const bool rg16 = e.rowgroup != nullptr && e.rowgroup_bf16;
+  if (!p.tma_store || e.act == TAIR_ACT_GEGLU || e.ln_row_stats != nullptr || p.N % 32 != 0 || p.splits != 1 ||
+      (e.bias != nullptr && !p.vec_bias) || (e.rowgroup != nullptr && !rg16) || (!lean && !rg16))
+    return 2;
+  if (e.residual == nullptr && !rg16) return 0;
+  if (e.act != TAIR_ACT_NONE || (e.residual != nullptr && rg16)) return 2;
+  if (rg16) return ((reinterpret_cast<uintptr_t>(e.rowgroup) % 16) == 0 && e.ldg % 8 == 0) ? 1 : 2;
+  return p.vec_res ? 1 : 2;
+}
+
 int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn, bool two,
              cudaStream_t st) {
   CUtensorMap tmB;
@@ -903,6 +1156,10 @@ int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, 
     if ((rc = make_tmap_bf16(&tmC64, p.epi.out, 2, dimsC, strC, box64, nullptr, 3))) return rc;
     if ((rc = make_tmap_bf16(&tmC32, p.epi.out, 2, dimsC, strC, box32, nullptr, 2))) return rc;
   }
+  p.epi_mode = pick_epi_mode(p);
+  TAIR_REQUIRE(!p.epi.rowgroup_bf16 || p.epi_mode == 1,
+               "bf16 row groups need the row-add epilogue: GEMM / conv with a 16-byte aligned bf16 output, N %% 32 == 0, "
+               "no activation, no residual, no folded LayerNorm, rows 16-byte aligned (ldg %% 8 == 0)");
   if (two) {
     switch (bn) {
       case 256: return launch_bn2<256>(tmA, tmB, tmC64, tmC32, p, st);
@@ -943,7 +1200,7 @@ int check_epilogue(const tair_epilogue* e, GemmParams& p, int n_out) {
   const int esz = e->out_fp32 ? 4 : 2;
   p.vec_out = ((reinterpret_cast<uintptr_t>(e->out) % 16) == 0) && ((e->ldc * esz) % 16 == 0);
   p.vec_bias = e->bias && ((reinterpret_cast<uintptr_t>(e->bias) % 16) == 0);
-  p.vec_rg = e->rowgroup && ((reinterpret_cast<uintptr_t>(e->rowgroup) % 16) == 0) && (e->ldg % 4 == 0);
+  p.vec_rg = e->rowgroup && !e->rowgroup_bf16 && ((reinterpret_cast<uintptr_t>(e->rowgroup) % 16) == 0) && (e->ldg % 4 == 0);
   p.vec_res = e->residual && ((reinterpret_cast<uintptr_t>(e->residual) % 16) == 0) &&
               ((e->ldr * 2) % 16 == 0);
   return TAIR_OK;
@@ -970,7 +1227,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, con
   }
   float v[4] = {acc.x, acc.y, acc.z, acc.w};
   const float* rg = e.rowgroup == nullptr ? nullptr
-                    : e.rowgroup + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
+                    : reinterpret_cast<const float*>(e.rowgroup) + (int64_t)(e.rows_per_group > 0 ? m / e.rows_per_group : m % (-e.rows_per_group)) * e.ldg;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (e.bias != nullptr) v[j] += __ldg(e.bias + n + j);
@@ -1004,6 +1261,7 @@ int dispatch(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, 
 // `ws` holds splits * M * N floats
 int dispatch_splitk(const CUtensorMap& tmA, const void* W, int64_t ldw, GemmParams& p, int bn, int splits,
                     cudaStream_t st, void* ws) {
+  TAIR_REQUIRE(!p.epi.rowgroup_bf16, "bf16 row groups are not supported by the split-K path");
   GemmParams q = p;
   q.splits = splits;
   q.kb_split = (p.num_kb + splits - 1) / splits;
@@ -1080,7 +1338,7 @@ int tuned_dispatch(const CUtensorMap& tmA, const void* A, size_t in_bytes, const
   cudaGetDevice(&key.dev);
   key.conv = p.conv; key.M = p.M; key.N = p.N; key.K = p.K; key.Wo = p.Wo; key.stride = p.stride; key.act = act;
   key.flags = (p.epi.out_fp32 ? 1 : 0) | (p.vec_out ? 2 : 0) | (p.epi.residual ? 4 : 0) | (p.epi.rowgroup ? 8 : 0) |
-              (p.epi.ln_row_stats ? 16 : 0);
+              (p.epi.ln_row_stats ? 16 : 0) | (p.epi.rowgroup_bf16 ? 32 : 0);
   {
     std::lock_guard<std::mutex> lk(g_tune_mu);
     auto it = g_tuned.find(key);

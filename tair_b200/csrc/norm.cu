@@ -325,6 +325,92 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld
 }
 
 
+// LayerNorm for narrow rows (C <= 512: TESTR's 256-wide tokens, 151552 rows per encoder layer): one warp per R2 rows with
+// ALL of a thread's loads issued before the first use, like row_stats_kernel.  With one row per warp a thread has a
+// single 16-byte load in flight and the kernel sits at half the HBM rate (45 us for 151552 x 256, floor 24).
+template <int VPL, int R2>
+__global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                      int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      int M, int C, float eps) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R2;
+  if (row0 >= M) return;
+  const int nvec = C >> 3;
+  uint4 raw[R2][VPL];
+#pragma unroll
+  for (int rr = 0; rr < R2; ++rr) {
+    const int row = row0 + rr < M ? row0 + rr : M - 1;   // clamp: rows past the end are loaded but not written
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lane + k * 32;
+      raw[rr][k] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * ldx + vi * 8)) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  float s[R2], q[R2];
+#pragma unroll
+  for (int rr = 0; rr < R2; ++rr) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
+      acc += ((a.x + a.y) + (b2.x + b2.y)) + ((c.x + c.y) + (d.x + d.y));
+    }
+    s[rr] = acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int rr = 0; rr < R2; ++rr) s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
+#pragma unroll
+  for (int rr = 0; rr < R2; ++rr) {
+    const float mean = s[rr] / (float)C;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (lane + k * 32 < nvec) {
+        const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
+        const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dd = f[i] - mean;
+          acc = fmaf(dd, dd, acc);
+        }
+      }
+    }
+    q[rr] = acc;
+    s[rr] = mean;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int rr = 0; rr < R2; ++rr) q[rr] += __shfl_xor_sync(0xffffffffu, q[rr], o);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int rr = 0; rr < R2; ++rr) {
+        if (row0 + rr < M) {
+          const float mean = s[rr], rstd = rsqrtf(q[rr] / (float)C + eps);
+          const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
+          const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+          float o8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = (f[i] - mean) * rstd * gg[i] + bb[i];   // same expression as layernorm_kernel
+          store8(y + (int64_t)(row0 + rr) * ldy + vi * 8, o8);
+        }
+      }
+    }
+  }
+}
+
 // LayerNorm over the first Cv channels of rows that are padded to C (C % 8 == 0, C <= 256): the SwinIR trunk keeps its
 // 180 channels in 192-wide rows so that every GEMM / conv operand is TMA-legal; pad channels are written as zeros.
 __global__ void layernorm_ragged_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
@@ -486,6 +572,13 @@ extern "C" int tair_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, 
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const int nvec = C / 8;
+  static int rows_mode = -1;   // TAIR_LN_ROWS=0: the one-row-per-warp kernel for every width (A/B probe)
+  if (rows_mode < 0) { const char* e = getenv("TAIR_LN_ROWS"); rows_mode = e ? atoi(e) : 1; }
+  if (rows_mode && nvec <= 32) {
+    TAIR_LAUNCH((layernorm_rows_kernel<1, 4>), (M + warps * 4 - 1) / (warps * 4), warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
+  } else if (rows_mode && nvec <= 64) {
+    TAIR_LAUNCH((layernorm_rows_kernel<2, 2>), (M + warps * 2 - 1) / (warps * 2), warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
+  } else
   if (nvec <= 32) TAIR_LAUNCH((layernorm_kernel<1>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   else if (nvec <= 64) TAIR_LAUNCH((layernorm_kernel<2>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);
   else if (nvec <= 160) TAIR_LAUNCH((layernorm_kernel<5>), grid, warps * 32, 0, st, xp, ldx, yp, ldy, gamma, beta, M, C, eps);

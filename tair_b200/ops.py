@@ -120,12 +120,15 @@ def _make_epilogue(out, M, n_out, bias, residual, rowgroup, rows_per_group, act)
             raise TairError(f"residual has shape {tuple(r2.shape)}, expected {(M, n_out)}")
         e.residual, e.ldr = r2.data_ptr(), ldr
     if rowgroup is not None:
-        _cuda(rowgroup, "rowgroup", torch.float32)
+        _cuda(rowgroup, "rowgroup")
+        if rowgroup.dtype not in (BF16, torch.float32):
+            raise TairError("rowgroup must be fp32 or bf16")
         g2, ldg = _rows(rowgroup, "rowgroup")
         covered = g2.shape[0] * rows_per_group >= M if rows_per_group > 0 else (rows_per_group < 0 and g2.shape[0] >= -rows_per_group)
         if not covered or g2.shape[1] < n_out:
             raise TairError("rowgroup shape does not cover the output")
         e.rowgroup, e.ldg, e.rows_per_group = g2.data_ptr(), ldg, rows_per_group
+        e.rowgroup_bf16 = 1 if rowgroup.dtype == BF16 else 0   # bf16 rows: prefetched row-add epilogue (see the header)
     return e
 
 

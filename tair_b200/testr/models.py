@@ -12,7 +12,7 @@ bbox_class == transformer.bbox_class_embed, bbox_coord == transformer.bbox_embed
 Execution differs from the eager reference (~3.8 k aten launches per step):
   * tokens stay bf16 row matrices [B*S, 256]; every Linear is ``tair_gemm_bf16`` with bias / ReLU / residual fused;
   * ``query + pos`` is never materialised: Linear(q + pos) = Linear(q) + Linear(pos), and Linear(pos) enters the GEMM
-    epilogue as a per-object (rows_per_group) or periodic row add; constant positional terms are folded at pack time;
+    epilogue as a per-object (rows_per_group) or periodic bf16 row add; constant positional terms are folded at pack time;
   * sampling_offsets | attention_weights are one GEMM whose fp32 rows feed ``tair_msda_fused`` (softmax, location
     arithmetic and the bilinear gather in one kernel);
   * nn.MultiheadAttention cores run on the tcgen05 attention kernel (``tair_attention_seq_bf16``) directly on the fused
@@ -32,6 +32,10 @@ from .. import ops
 from ..model.util import BF16, Conv1x1, Conv3x3, GroupNorm, LayerNorm, Linear
 
 F32 = torch.float32
+import os as _os
+# Positional projection rows entering the GEMM epilogues: bf16 rows ride the prefetched row-add epilogue
+# (tair_epilogue.rowgroup_bf16) at half the L2 traffic; TAIR_TESTR_ROWS_FP32=1 keeps the fp32 rows (A/B probe).
+ROW_DTYPE = F32 if _os.environ.get("TAIR_TESTR_ROWS_FP32", "0") == "1" else BF16
 
 
 class MLP(nn.Module):
@@ -346,7 +350,7 @@ class TESTR(nn.Module):
             enc_pos_rows = []
             for layer in T.encoder.layers:
                 _, w32, b32 = layer.self_attn.cat_weight()
-                enc_pos_rows.append((pos @ w32.t() + b32).contiguous())                                  # [S,384]
+                enc_pos_rows.append((pos @ w32.t() + b32).to(ROW_DTYPE).contiguous())                    # [S,384]
             n_ch, d = self.max_text_len, self.d_model
             p1 = torch.arange(1, n_ch + 1, device=device).float()
             p1 = p1 / (p1[-1:] + 1e-6) * self.pos_embed_scale
@@ -356,7 +360,8 @@ class TESTR(nn.Module):
             for layer in T.decoder.layers:
                 _, _, wqk32, b_in, _, _ = layer.attn_intra_text.packed()
                 _, wc32, bc32 = layer.attn_cross_text.cat_weight()
-                dec_text_rows.append(((text_pos @ wqk32.t() + b_in).contiguous(), (text_pos @ wc32.t() + bc32).contiguous()))
+                dec_text_rows.append(((text_pos @ wqk32.t() + b_in).to(ROW_DTYPE).contiguous(),
+                                      (text_pos @ wc32.t() + bc32).to(ROW_DTYPE).contiguous()))
             c = dict(stamp=st, S=S, shapes=shp, starts=starts, enc_ref=enc_ref, props_logit=props_logit,
                      valid=valid.to(BF16), enc_pos_rows=enc_pos_rows, dec_text_rows=dec_text_rows,
                      dim_t=10000 ** (2 * torch.div(torch.arange(64, dtype=F32, device=device), 2, rounding_mode="trunc") / 64))
@@ -402,9 +407,9 @@ class TESTR(nn.Module):
         boxes_ref = boxes[:, :, None, :].expand(B, n_obj, self.num_feature_levels, 4).contiguous()
         for layer, (txt_qk, txt_cross) in zip(T.decoder.layers, c["dec_text_rows"]):
             _, wqk_bf16, _, b_in, _, _ = layer.attn_intra.packed()
-            loc_qk = ops.gemm(qpos, wqk_bf16, bias=b_in, out_dtype=F32)                                  # [B*100,768]
+            loc_qk = ops.gemm(qpos, wqk_bf16, bias=b_in, out_dtype=ROW_DTYPE)                            # [B*100,768]
             wc_bf16, _, bc = layer.attn_cross.cat_weight()
-            loc_cross = ops.gemm(qpos, wc_bf16, bias=bc, out_dtype=F32)                                  # [B*100,384]
+            loc_cross = ops.gemm(qpos, wc_bf16, bias=bc, out_dtype=ROW_DTYPE)                            # [B*100,384]
             tgt = layer.branch("", tgt, B, n_obj, n_pt, loc_qk, loc_cross, n_pt, mem, c["shapes"], c["starts"], boxes_ref)
             tgt_text = layer.branch("_text", tgt_text, B, n_obj, n_ch, txt_qk, txt_cross, -n_ch, mem, c["shapes"],
                                     c["starts"], boxes_ref)

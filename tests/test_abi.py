@@ -41,7 +41,7 @@ def test_ctypes_table_matches_header():
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.tair_abi_version() == 3
+    assert lib.tair_abi_version() == 4
     assert isinstance(lib.tair_last_error(), bytes)
 
 

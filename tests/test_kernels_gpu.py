@@ -54,6 +54,57 @@ def test_gemm_epilogues(ops):
     assert rel(ops.gemm(a_wide[:, 128:], w), a_wide[:, 128:].float() @ w.float().t()) < BF16_TOL
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 256), (5000, 384, 256), (3000, 1536, 256), (2500, 1024, 256),
+                                   (4096, 320, 320), (2048, 640, 640), (1000, 1280, 1280), (300, 96, 64),
+                                   (9472, 160, 256), (1111, 224, 128)])
+def test_gemm_lean_epilogue_variants(ops, M, N, K):
+    """The specialised TMA-store epilogues (csrc/gemm_tc.cu: epilogue_tile_tma_lean): plain, bias, bias + activation,
+    bias + residual, residual alone, and bf16 row-group rows in both addressing forms, at the N tiles the tuner may pick
+    (N % 32 == 0 selects them; ragged M exercises the row clipping)."""
+    a, w = rn(M, K).bfloat16(), rn(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    bias, res = rn(N, seed=2), rn(M, N, seed=3).bfloat16()
+    raw = a.float() @ w.float().t()
+    base = raw + bias
+    assert rel(ops.gemm(a, w), raw) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias), base) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, act=ops.ACT_RELU), F.relu(base)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(base)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, act=ops.ACT_SILU), F.silu(base)) < BF16_TOL
+    assert rel(ops.gemm(a, w, bias=bias, residual=res), base + res.float()) < BF16_TOL
+    assert rel(ops.gemm(a, w, residual=res), raw + res.float()) < BF16_TOL
+    # residual aliasing the output (x = x + f(x), the transformer blocks' pattern)
+    buf = res.clone()
+    ops.gemm(a, w, bias=bias, residual=buf, out=buf)
+    assert rel(buf, base + res.float()) < BF16_TOL
+    # bf16 row groups: one row per group of consecutive output rows / periodic rows
+    per = 25
+    G = (M + per - 1) // per
+    rg = rn(G, N, seed=4).bfloat16()
+    want = raw + rg.float().repeat_interleave(per, 0)[:M]
+    assert rel(ops.gemm(a, w, rowgroup=rg, rows_per_group=per), want) < BF16_TOL
+    P = 100
+    rgp = rn(P, N, seed=5).bfloat16()
+    want = raw + rgp.float()[torch.arange(M, device="cuda") % P] + bias
+    assert rel(ops.gemm(a, w, bias=bias, rowgroup=rgp, rows_per_group=-P), want) < BF16_TOL
+    # the fp32 form of the same rows goes through the generic epilogue and must agree to bf16 rounding of the rows
+    got32 = ops.gemm(a, w, bias=bias, rowgroup=rgp.float(), rows_per_group=-P)
+    assert rel(got32, want) < BF16_TOL
+
+
+def test_gemm_bf16_rowgroup_limits(ops):
+    """bf16 row groups exist only in the row-add epilogue: combinations it does not cover fail loudly."""
+    from tair_b200._lib import TairError
+    M, N, K = 512, 256, 256
+    a, w = rn(M, K).bfloat16(), rn(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    rg = rn(4, N, seed=2).bfloat16()
+    for kw in (dict(act=ops.ACT_RELU), dict(residual=rn(M, N, seed=3).bfloat16()), dict(out_dtype=torch.float32)):
+        with pytest.raises(TairError):
+            ops.gemm(a, w, rowgroup=rg, rows_per_group=128, **kw)
+    w2 = rn(72, K, scale=K ** -0.5, seed=1).bfloat16()       # N % 32 != 0
+    with pytest.raises(TairError):
+        ops.gemm(a, w2, rowgroup=rn(4, 72, seed=2).bfloat16(), rows_per_group=128)
+
+
 def test_gemm_geglu_matches_chunked_reference(ops):
     from tair_b200.model.attention import interleave_geglu
     M, C = 1000, 320
@@ -128,7 +179,8 @@ def test_groupnorm(ops, B, HW, C, eps, act):
     assert rel(out, ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (333, 1280), (9472, 256), (7, 2048)])
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (333, 1280), (9472, 256), (7, 2048), (1001, 256), (3, 64),
+                                 (2501, 512), (77, 384), (5, 8)])
 def test_layernorm(ops, M, C):
     x = (rn(M, C) * 2 + 0.3).bfloat16()
     g, b = 1 + 0.1 * rn(C, seed=1), 0.1 * rn(C, seed=2)
