@@ -226,6 +226,14 @@ int tair_attention_seq_bf16(const void* q, const void* k, const void* v, int64_t
                             int32_t L, int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride,
                             int64_t tok_stride, float scale, void* stream);
 
+/* The same, for 32-wide heads and sequences of at most 128 tokens, on UNPADDED projections (head h in columns
+ * [32h, 32h + 32) of q / k / v / o; ld >= 32 H).  This is what the TESTR decoder calls: 16 control points / 25 characters
+ * per object, 100 objects per tile, 8 heads of 32 channels - far below one 128-row tensor-core tile, so the kernel is
+ * register-level mma.sync per (sequence, head) and bound by the bytes it reads (csrc/attn_small.cu). */
+int tair_attention_seq32_bf16(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int32_t H,
+                              int32_t L, int64_t n_outer, int32_t n_inner, int64_t outer_stride, int64_t inner_stride,
+                              int64_t tok_stride, float scale, void* stream);
+
 /* Detection post-processing of the TESTR head (transformer_detector.py:123-152 + spaced_sampler.py:298-306) for n_items =
  * tiles x queries: scores[i] = sigmoid(mean_p pred_logits[i,p]) (one class), polygons[i, 2p+{0,1}] = ctrl point p in pixels
  * (x * image_w, y * image_h), recs[i,c] = arg-max character of position c (uint8).  pred_logits fp32 [n_items, n_pts],

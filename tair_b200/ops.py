@@ -498,6 +498,33 @@ def attention_seq(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_in
     return out
 
 
+def attention_seq32(qkv: torch.Tensor, *, n_heads: int, L: int, n_outer: int, n_inner: int, outer_stride: int,
+                    inner_stride: int, tok_stride: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Self-attention over many short (L <= 128) strided sequences with 32-wide heads on UNPADDED projections: qkv bf16
+    [rows, 3*H*32] (q | k | v); returns [rows, H*32] in the same row order (csrc/attn_small.cu)."""
+    _cuda(qkv, "qkv", BF16)
+    q2, ld = _rows(qkv, "qkv")
+    E = n_heads * 32
+    if q2.shape[1] != 3 * E:
+        raise TairError(f"attention_seq32: expected {3 * E} columns, got {q2.shape[1]}")
+    last = (n_outer - 1) * outer_stride + (n_inner - 1) * inner_stride + (L - 1) * tok_stride
+    if min(n_outer, n_inner, L, tok_stride) < 1 or min(outer_stride, inner_stride) < 0 or last >= q2.shape[0]:
+        raise TairError("attention_seq32: the sequence addressing leaves the qkv rows")
+    if out is None:
+        out = torch.empty((q2.shape[0], E), device=qkv.device, dtype=BF16)
+    _cuda(out, "out", BF16)
+    o2, ldo = _rows(out, "out")
+    if o2.shape[0] != q2.shape[0] or o2.shape[1] != E:
+        raise TairError(f"attention_seq32: out must be [{q2.shape[0]}, {E}]")
+    base = q2.data_ptr()
+    with _timed("attention_seq", 4.0 * n_outer * n_inner * n_heads * L * L * 32, (n_outer, n_inner, n_heads, L)):
+        rc = _lib.lib().tair_attention_seq32_bf16(base, base + 2 * E, base + 4 * E, ld, o2.data_ptr(), ldo, n_heads, L,
+                                                  n_outer, n_inner, outer_stride, inner_stride, tok_stride, float(scale),
+                                                  _stream())
+    _lib.check(rc, "tair_attention_seq32_bf16")
+    return out
+
+
 def tiles_bicubic(image_u8: torch.Tensor, origins: torch.Tensor, bounds: torch.Tensor, coeffs: torch.Tensor,
                   tile: int, out_size: int) -> torch.Tensor:
     """image_u8 [Hp,Wp,3] uint8 (zero-padded LQ), origins [P,2] int32 (y,x) -> [P,3,out,out] fp32 in [0,1],

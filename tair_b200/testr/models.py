@@ -15,8 +15,9 @@ Execution differs from the eager reference (~3.8 k aten launches per step):
     epilogue as a per-object (rows_per_group) or periodic bf16 row add; constant positional terms are folded at pack time;
   * sampling_offsets | attention_weights are one GEMM whose fp32 rows feed ``tair_msda_fused`` (softmax, location
     arithmetic and the bilinear gather in one kernel);
-  * nn.MultiheadAttention cores run on the tcgen05 attention kernel (``tair_attention_seq_bf16``) directly on the fused
-    in_proj rows with strided sequence addressing, so the intra/inter swapdims (:454-466) are free;
+  * nn.MultiheadAttention cores (sequences of 16 / 25 / 100 tokens, 32-wide heads) run on ``tair_attention_seq32_bf16``
+    directly on the fused, unpadded in_proj rows with strided sequence addressing, so the intra/inter swapdims
+    (:454-466) are free;
   * only the last decoder layer's heads are evaluated (inference reads ``[-1]`` only, models.py:156-158).
 Masks are all-False on this path (models.py:127), so valid ratios are 1.
 """
@@ -36,6 +37,9 @@ import os as _os
 # Positional projection rows entering the GEMM epilogues: bf16 rows ride the prefetched row-add epilogue
 # (tair_epilogue.rowgroup_bf16) at half the L2 traffic; TAIR_TESTR_ROWS_FP32=1 keeps the fp32 rows (A/B probe).
 ROW_DTYPE = F32 if _os.environ.get("TAIR_TESTR_ROWS_FP32", "0") == "1" else BF16
+# The decoder's nn.MultiheadAttention cores (32-wide heads, sequences of 16 / 25 / 100 tokens): the register-level kernel on
+# unpadded projections (csrc/attn_small.cu); TAIR_TESTR_ATTN64=1 keeps the tcgen05 kernel on 64-column head slots (A/B probe).
+SMALL_ATTN = _os.environ.get("TAIR_TESTR_ATTN64", "0") != "1"
 
 
 class MLP(nn.Module):
@@ -157,6 +161,36 @@ class MultiheadAttention(nn.Module):
             self._pk_stamp = st
         return self._pk
 
+    def packed32(self):
+        """Unpadded kernel layout for 32-wide heads (``ops.attention_seq32``), same tuple order as ``packed``:
+        (in_proj bf16 [3E, E], the same with the V rows zeroed in bf16 and fp32, fp32 bias [3E], out_proj weight bf16
+        [E, E], out_proj bias fp32)."""
+        st = (self.in_proj_weight.data_ptr(), self.in_proj_weight._version, self.in_proj_bias._version,
+              self.out_proj._stamp())
+        if getattr(self, "_pk32_stamp", None) != st:
+            with torch.no_grad():
+                E = self.embed_dim
+                assert E // self.num_heads == 32
+                w = self.in_proj_weight.detach().float()
+                wqk = w.clone()
+                wqk[2 * E:] = 0
+                self._pk32 = (w.to(BF16).contiguous(), wqk.to(BF16).contiguous(), wqk.contiguous(),
+                              self.in_proj_bias.detach().float().contiguous(),
+                              self.out_proj.weight.detach().to(BF16).contiguous(),
+                              self.out_proj.bias.detach().float().contiguous())
+            self._pk32_stamp = st
+        return self._pk32
+
+    def pack(self):
+        return self.packed32() if SMALL_ATTN and self.embed_dim // self.num_heads == 32 else self.packed()
+
+    def core(self, qkv, **kw):
+        """softmax(q k^T / sqrt(d)) v on the fused in_proj rows; strided sequence addressing in ``kw``."""
+        if SMALL_ATTN and self.embed_dim // self.num_heads == 32:
+            return ops.attention_seq32(qkv, n_heads=self.num_heads, scale=self.scale, **kw)
+        return ops.attention_seq(qkv, n_heads=self.num_heads, scale=self.scale,
+                                 real_head_dim=self.embed_dim // self.num_heads, **kw)
+
     @property
     def scale(self) -> float:
         return (self.embed_dim // self.num_heads) ** -0.5
@@ -209,15 +243,13 @@ class CompositeDecoderLayer(nn.Module):
         (bias included) entering the in_proj / sampling projections; rpg = n_pt (per object) or -n_pt (periodic)."""
         g = lambda name: getattr(self, name + sfx)  # noqa: E731
         intra, inter, cross = g("attn_intra"), g("attn_inter"), g("attn_cross")
-        w_in, _, _, _, w_out, b_out = intra.packed()
+        w_in, _, _, _, w_out, b_out = intra.pack()
         qkv = ops.gemm(tgt, w_in, rowgroup=qk_rows, rows_per_group=rpg)
-        a = ops.attention_seq(qkv, n_heads=self.n_heads, L=n_pt, n_outer=B * n_obj, n_inner=1, outer_stride=n_pt,
-                              inner_stride=0, tok_stride=1, scale=intra.scale, real_head_dim=256 // self.n_heads)
+        a = intra.core(qkv, L=n_pt, n_outer=B * n_obj, n_inner=1, outer_stride=n_pt, inner_stride=0, tok_stride=1)
         tgt = g("norm_intra")(ops.gemm(a, w_out, bias=b_out, residual=tgt))
-        w_in, _, _, b_in, w_out, b_out = inter.packed()
+        w_in, _, _, b_in, w_out, b_out = inter.pack()
         qkv = ops.gemm(tgt, w_in, bias=b_in)
-        a = ops.attention_seq(qkv, n_heads=self.n_heads, L=n_obj, n_outer=B, n_inner=n_pt, outer_stride=n_obj * n_pt,
-                              inner_stride=1, tok_stride=n_pt, scale=inter.scale, real_head_dim=256 // self.n_heads)
+        a = inter.core(qkv, L=n_obj, n_outer=B, n_inner=n_pt, outer_stride=n_obj * n_pt, inner_stride=1, tok_stride=n_pt)
         tgt = g("norm_inter")(ops.gemm(a, w_out, bias=b_out, residual=tgt))
         a = cross.core(tgt, cross_rows, rpg, mem, B, n_obj * n_pt, shapes, starts, boxes_ref, False, n_pt)
         tgt = g("norm_cross")(cross.output_proj(a, residual=tgt))
@@ -358,7 +390,7 @@ class TESTR(nn.Module):
             text_pos = torch.cat((sin_inp.sin(), sin_inp.cos()), dim=-1)[:, :d]                          # [25,256]
             dec_text_rows = []
             for layer in T.decoder.layers:
-                _, _, wqk32, b_in, _, _ = layer.attn_intra_text.packed()
+                _, _, wqk32, b_in, _, _ = layer.attn_intra_text.pack()
                 _, wc32, bc32 = layer.attn_cross_text.cat_weight()
                 dec_text_rows.append(((text_pos @ wqk32.t() + b_in).to(ROW_DTYPE).contiguous(),
                                       (text_pos @ wc32.t() + bc32).to(ROW_DTYPE).contiguous()))
@@ -406,7 +438,7 @@ class TESTR(nn.Module):
         tgt_text = self.text_embed.weight.to(BF16)[None].expand(B * n_obj, n_ch, d).reshape(-1, d).contiguous()
         boxes_ref = boxes[:, :, None, :].expand(B, n_obj, self.num_feature_levels, 4).contiguous()
         for layer, (txt_qk, txt_cross) in zip(T.decoder.layers, c["dec_text_rows"]):
-            _, wqk_bf16, _, b_in, _, _ = layer.attn_intra.packed()
+            _, wqk_bf16, _, b_in, _, _ = layer.attn_intra.pack()
             loc_qk = ops.gemm(qpos, wqk_bf16, bias=b_in, out_dtype=ROW_DTYPE)                            # [B*100,768]
             wc_bf16, _, bc = layer.attn_cross.cat_weight()
             loc_cross = ops.gemm(qpos, wc_bf16, bias=bc, out_dtype=ROW_DTYPE)                            # [B*100,384]

@@ -93,6 +93,48 @@ def test_attention_seq_padded_heads_vs_torch(cuda_lib, L, n_outer, n_inner):
     assert rel(got[..., :32], ref) < 1e-2
 
 
+@pytest.mark.parametrize("L,n_outer,n_inner", [(16, 200, 1), (25, 301, 1), (100, 3, 25), (100, 2, 16), (7, 33, 1),
+                                               (128, 5, 1), (33, 9, 2), (1, 5, 1)])
+def test_attention_seq32_unpadded_heads_vs_torch(cuda_lib, L, n_outer, n_inner):
+    """Register-level attention on strided short sequences, 32-wide heads on unpadded rows (csrc/attn_small.cu):
+    the decoder's shapes (16 / 25 tokens per object, 100 objects per tile), odd lengths, the 128-token limit, and
+    scores large enough that the running-max subtraction matters."""
+    import torch.nn.functional as F
+    from tair_b200 import ops
+    H = 8
+    g = torch.Generator(device="cuda").manual_seed(L)
+    rows = n_outer * L * n_inner
+    real = (torch.randn(rows, 3, H, 32, device="cuda", generator=g) * 2.0).bfloat16()
+    qkv = real.view(rows, 3 * H * 32)
+    out = torch.full((rows, H * 32), 7.0, device="cuda", dtype=torch.bfloat16)
+    if n_inner == 1:
+        ops.attention_seq32(qkv, n_heads=H, L=L, n_outer=n_outer, n_inner=1, outer_stride=L, inner_stride=0, tok_stride=1,
+                            scale=32 ** -0.5, out=out)
+        x = real.float().view(n_outer, L, 3, H, 32)
+    else:
+        ops.attention_seq32(qkv, n_heads=H, L=L, n_outer=n_outer, n_inner=n_inner, outer_stride=L * n_inner,
+                            inner_stride=1, tok_stride=n_inner, scale=32 ** -0.5, out=out)
+        x = real.float().view(n_outer, L, n_inner, 3, H, 32).permute(0, 2, 1, 3, 4, 5).reshape(n_outer * n_inner, L, 3, H, 32)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2)          # [seq, L, H, 32]
+    if n_inner > 1:
+        ref = ref.reshape(n_outer, n_inner, L, H, 32).permute(0, 2, 1, 3, 4)
+    assert rel(out.view(rows, H, 32), ref.reshape(rows, H, 32)) < 1e-2
+
+
+def test_attention_seq32_limits(cuda_lib):
+    from tair_b200 import ops
+    from tair_b200._lib import TairError
+    qkv = torch.zeros(200 * 8, 768, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(TairError):      # longer than 128 tokens
+        ops.attention_seq32(qkv, n_heads=8, L=200, n_outer=8, n_inner=1, outer_stride=200, inner_stride=0, tok_stride=1, scale=1.0)
+    with pytest.raises(TairError):      # addressing past the last row
+        ops.attention_seq32(qkv, n_heads=8, L=100, n_outer=17, n_inner=1, outer_stride=100, inner_stride=0, tok_stride=1, scale=1.0)
+    with pytest.raises(TairError):      # 64-column head slots are the other kernel's layout
+        ops.attention_seq32(torch.zeros(64, 1536, device="cuda", dtype=torch.bfloat16), n_heads=8, L=16, n_outer=4, n_inner=1,
+                            outer_stride=16, inner_stride=0, tok_stride=1, scale=1.0)
+
+
 def test_msdeformattn_module_dropin_signature(detector):
     """MSDeformAttn.forward(query, reference_points, input_flatten, shapes, level_start, mask) — ms_deform_attn.py:116."""
     from oracle import msda
