@@ -125,6 +125,7 @@ struct MsdaFusedParams {
   __nv_bfloat16* out;          // [B*Lq, M*D]
   int B, S, M, D, L, Lq, P;
   int lanes_per_item;
+  int wide_loads;              // 1: 32-byte (LDG.256) corner loads are legal for this launch
   long items;
 };
 
@@ -214,6 +215,12 @@ __global__ void __launch_bounds__(256) msda_fused_kernel(const MsdaFusedParams p
 // slots 45 % busy, L2 6 % busy: bound by its own instruction stream, not by the gather.  Here: 16-byte loads of the
 // offset / logit row, corner validity folded into the bilinear weights with clamped (always legal) addresses instead of
 // per-corner branches and zero fills, 32-bit offsets inside an image, <= 64 registers for 4 CTAs per SM. ----
+__device__ __forceinline__ void ldg256(const void* ptr, uint32_t (&r)[8]) {   // 32-byte aligned, read-only path
+  asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "l"(ptr));
+}
+
 template <typename PJ> struct ProjVec;
 template <> struct ProjVec<float> {
   static constexpr int PER = 4;  // values per 16-byte load
@@ -306,6 +313,24 @@ __global__ void __launch_bounds__(256, CPL == 8 ? 4 : 3) msda_fused44_kernel(con
       const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_low + 1, 0), W - 1);
       const uint32_t r0 = (uint32_t)y0 * wrs, r1 = (uint32_t)y1 * wrs, c0 = (uint32_t)x0 * rsb, c1 = (uint32_t)x1 * rsb;
       const float w1 = wt * wl, w2 = wt * wr, w3 = wb * wl, w4 = wb * wr;
+      if constexpr (CPL == 16) {
+        if (p.wide_loads) {
+          // one 32-byte load per corner (LDG.256, sm_100): this lane's 16 channels are exactly one sector, so the gather
+          // issues half the L1 requests of two 16-byte loads (each of which touched the sector for half of its bytes)
+          uint32_t a1[8], a2[8], a3[8], a4[8];
+          ldg256(vlb + (r0 + c0), a1);
+          ldg256(vlb + (r0 + c1), a2);
+          ldg256(vlb + (r1 + c0), a3);
+          ldg256(vlb + (r1 + c1), a4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 v1 = unpack_bf16(a1[i]), v2 = unpack_bf16(a2[i]), v3 = unpack_bf16(a3[i]), v4 = unpack_bf16(a4[i]);
+            acc[2 * i] = fmaf(w4, v4.x, fmaf(w3, v3.x, fmaf(w2, v2.x, fmaf(w1, v1.x, acc[2 * i]))));
+            acc[2 * i + 1] = fmaf(w4, v4.y, fmaf(w3, v3.y, fmaf(w2, v2.y, fmaf(w1, v1.y, acc[2 * i + 1]))));
+          }
+          continue;
+        }
+      }
 #pragma unroll
       for (int nv = 0; nv < NV; ++nv) {
         const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(vlb + (r0 + c0)) + nv);
@@ -389,6 +414,8 @@ extern "C" int tair_msda_fused(const void* value, const int64_t* spatial_shapes,
   p.B = B; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P;
   p.lanes_per_item = D / 8;
   p.items = (long)B * Lq * M;
+  // 32-byte loads need 32-byte aligned taps: value base and the per-head row (D * 2 bytes) multiples of 32
+  p.wide_loads = ((reinterpret_cast<uintptr_t>(value) % 32) == 0 && (D * 2) % 32 == 0 && !getenv("TAIR_MSDA_LDG128")) ? 1 : 0;
   const long threads_total = p.items * p.lanes_per_item;
   const long grid = (threads_total + 255) / 256;
   TAIR_REQUIRE(grid < (1l << 31), "msda_fused: problem too large");
