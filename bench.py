@@ -355,6 +355,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    last_local_ms = [0.0]
+
     def timed(fn, k):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -364,6 +366,7 @@ def main():
         b.record()
         barrier()
         ms = a.elapsed_time(b) / k
+        last_local_ms[0] = ms
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -377,6 +380,12 @@ def main():
     with ClockSampler(local) as clk:
         ms, z = timed(step_resident, K)
     clocks = clk.summary()
+    per_rank = None
+    if world > 1:   # which rank sets the max: per-rank time and SM clock of the headline region (GPUs of one box differ by 1-3 %)
+        mine = torch.tensor([last_local_ms[0], float(clocks.get("sm_mhz") or 0.0)], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_denoise": [round(float(t[0]), 2) for t in allr], "sm_mhz": [float(t[1]) for t in allr]}
     for _ in range(1):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, K)
@@ -451,7 +460,7 @@ def main():
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches_per_step * SAMPLER_STEPS * K),
             "gpu_launches_per_denoise_step": int(launches_per_step),
-            "clocks": clocks, "roofline": roofline, "kernel_breakdown_one_step": breakdown, "norm_families": norms}
+            "clocks": clocks, "per_rank": per_rank, "roofline": roofline, "kernel_breakdown_one_step": breakdown, "norm_families": norms}
 
     if extras:
         from types import SimpleNamespace
