@@ -39,7 +39,8 @@ for bsz in [int(v) for v in os.environ.get("BATCHES", "4,16,32").split(",")]:
         return pipeline.restore_image(lq, model, sampler, steps=50, tile_batch=bsz, cfg_scale=4.0, uncond_fn=uncond_fn,
                                       cleaner=lambda x: cleaner(x).clamp(0, 1))
     if os.environ.get("WARM", "1") == "1":
-        pipeline.restore_image(lq[:128 * 2, :128 * max(2, bsz)], model, sampler, steps=2, tile_batch=bsz, cfg_scale=4.0,
+        wrows = max(2, -(-world * bsz // 35))          # enough 35-tile rows that every rank sees one full batch of bsz tiles
+        pipeline.restore_image(lq[:(wrows - 1) * 112 + 128], model, sampler, steps=2, tile_batch=bsz, cfg_scale=4.0,
                                uncond_fn=uncond_fn, cleaner=lambda x: cleaner(x).clamp(0, 1))   # graph capture / tuning
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
