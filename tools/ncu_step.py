@@ -14,6 +14,7 @@ dev = torch.device("cuda:0")
 model = ControlLDM(*full_cfgs()).to(dev).eval()
 nondegenerate_init_(model, 1234)
 model.overlap_controlnet = False   # one stream: ncu serialises kernels anyway, keep the launch order canonical
+model.return_nhwc_feats = True     # as SpacedSampler.sample / val_sample run it: decoder features stay channels-last bf16
 s = SpacedSampler(val_diffusion().betas, "v", False)
 s.make_schedule(50); s.to(dev)
 g = torch.Generator(device=dev).manual_seed(100)
