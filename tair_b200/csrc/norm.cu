@@ -347,6 +347,10 @@ __global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, int64
       raw[rr][k] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * ldx + vi * 8)) : make_uint4(0, 0, 0, 0);
     }
   }
+  // unpacked ONCE and kept in registers (ncu: the first version, which unpacked the bf16 words in each of its three
+  // passes, had its issue slots 72 % busy at 43 % of the DRAM rate); the second pass overwrites f with f - mean, which
+  // is also what the output pass needs
+  float f[R2][VPL][8];
   float s[R2], q[R2];
 #pragma unroll
   for (int rr = 0; rr < R2; ++rr) {
@@ -354,6 +358,8 @@ __global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, int64
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
+      f[rr][k][0] = a.x; f[rr][k][1] = a.y; f[rr][k][2] = b2.x; f[rr][k][3] = b2.y;
+      f[rr][k][4] = c.x; f[rr][k][5] = c.y; f[rr][k][6] = d.x; f[rr][k][7] = d.y;
       acc += ((a.x + a.y) + (b2.x + b2.y)) + ((c.x + c.y) + (d.x + d.y));
     }
     s[rr] = acc;
@@ -368,18 +374,15 @@ __global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, int64
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      if (lane + k * 32 < nvec) {
-        const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
-        const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+      const bool live = lane + k * 32 < nvec;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float dd = f[i] - mean;
-          acc = fmaf(dd, dd, acc);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float dd = f[rr][k][i] - mean;
+        f[rr][k][i] = dd;
+        if (live) acc = fmaf(dd, dd, acc);
       }
     }
     q[rr] = acc;
-    s[rr] = mean;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -398,12 +401,10 @@ __global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, int64
 #pragma unroll
       for (int rr = 0; rr < R2; ++rr) {
         if (row0 + rr < M) {
-          const float mean = s[rr], rstd = rsqrtf(q[rr] / (float)C + eps);
-          const float2 a = unpack_bf16(raw[rr][k].x), b2 = unpack_bf16(raw[rr][k].y), c = unpack_bf16(raw[rr][k].z), d = unpack_bf16(raw[rr][k].w);
-          const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+          const float rstd = rsqrtf(q[rr] / (float)C + eps);
           float o8[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o8[i] = (f[i] - mean) * rstd * gg[i] + bb[i];   // same expression as layernorm_kernel
+          for (int i = 0; i < 8; ++i) o8[i] = f[rr][k][i] * rstd * gg[i] + bb[i];   // same expression as layernorm_kernel
           store8(y + (int64_t)(row0 + rr) * ldy + vi * 8, o8);
         }
       }
