@@ -224,7 +224,8 @@ class FrozenOpenCLIPEmbedder(nn.Module):
         for t in new:
             self._cache[t] = self._free.pop()
         # one small H2D carries both index lists; rows are copied in and gathered out on the device
-        idx = torch.tensor([self._cache[t] for t in new] + [self._cache[t] for t in text], device=self._rows.device)
+        idx = torch.tensor([self._cache[t] for t in new] + [self._cache[t] for t in text], dtype=torch.long,
+                           device=self._rows.device)
         if new:
             self.prompts_encoded += len(new)
             z = self(self._tokenizer(new).to(self._rows.device), borrow=True, stamp=stamp)
