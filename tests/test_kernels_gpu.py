@@ -91,6 +91,27 @@ def test_gemm_lean_epilogue_variants(ops, M, N, K):
     assert rel(got32, want) < BF16_TOL
 
 
+def test_gemm_row_add_full_size_properties(ops):
+    """The K = 256 GEMMs of a B=16 TESTR encoder layer (151552 rows): the row-add epilogue is linear in what it adds -
+    gemm(a, w, residual=r) - gemm(a, w) reproduces r, the periodic bf16 row group reproduces its table on every image -
+    and tiles past the last full one (151552 = 1184 x 128 exactly; 151500 is ragged) are clipped, not overrun."""
+    K = N = 256
+    for M in (151552, 151500):
+        a, w = rn(M, K, seed=7).bfloat16(), rn(N, K, scale=K ** -0.5, seed=8).bfloat16()
+        plain = ops.gemm(a, w).float()
+        r = rn(M, N, seed=9).bfloat16()
+        canary = torch.full((M + 128, N), 3.0, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, residual=r, out=canary[:M])
+        assert (canary[M:] == 3.0).all()
+        d = canary[:M].float() - plain
+        assert (d - r.float()).abs().max() <= 2 ** -7 * (plain.abs().max() + r.float().abs().max())   # two bf16 roundings
+        S = 9472
+        table = rn(S, N, seed=10).bfloat16()
+        got = ops.gemm(a, w, rowgroup=table, rows_per_group=-S).float() - plain
+        want = table.float()[torch.arange(M, device="cuda") % S]
+        assert (got - want).abs().max() <= 2 ** -7 * (plain.abs().max() + want.abs().max())
+
+
 def test_gemm_bf16_rowgroup_limits(ops):
     """bf16 row groups exist only in the row-add epilogue: combinations it does not cover fail loudly."""
     from tair_b200._lib import TairError

@@ -122,6 +122,33 @@ def test_attention_seq32_unpadded_heads_vs_torch(cuda_lib, L, n_outer, n_inner):
     assert rel(out.view(rows, H, 32), ref.reshape(rows, H, 32)) < 1e-2
 
 
+def test_attention_seq32_full_size_properties(cuda_lib):
+    """At the sizes of a B=16 TESTR decoder layer (1600 objects x 25 characters, then 16 x 25 groups of 100 objects):
+    permuting the keys / values of every sequence leaves the output unchanged up to the bf16 rounding of P (softmax is a
+    set function), identical value rows are reproduced (a convex combination of equal rows), and repeating the launch is
+    bit-identical."""
+    from tair_b200 import ops
+    H, E = 8, 256
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (L, n_outer, n_inner, os_, is_, ts_) in ((25, 1600, 1, 25, 0, 1), (100, 16, 25, 2500, 1, 25)):
+        rows = 40000
+        qkv = torch.randn(rows, 3 * E, device="cuda", generator=g).bfloat16()
+        kw = dict(n_heads=H, L=L, n_outer=n_outer, n_inner=n_inner, outer_stride=os_, inner_stride=is_, tok_stride=ts_, scale=32 ** -0.5)
+        out = ops.attention_seq32(qkv, **kw)
+        assert torch.equal(out, ops.attention_seq32(qkv, **kw))
+        # permute the tokens of every sequence in K and V only (same permutation for both)
+        perm = torch.randperm(L, device="cuda", generator=g)
+        v5 = qkv.view(n_outer, L, n_inner, 3 * E) if n_inner > 1 else qkv.view(n_outer, L, 1, 3 * E)
+        shuf = v5.clone()
+        shuf[..., E:] = v5[:, perm][..., E:]
+        out_p = ops.attention_seq32(shuf.view(rows, 3 * E).contiguous(), **kw)
+        assert rel(out_p, out) < 1e-2
+        const = qkv.clone()
+        const[:, 2 * E:] = torch.randn(1, E, device="cuda", generator=g).bfloat16()      # every value row identical
+        out_c = ops.attention_seq32(const, **kw)
+        assert rel(out_c, const[:, 2 * E:]) < 1e-2
+
+
 def test_attention_seq32_limits(cuda_lib):
     from tair_b200 import ops
     from tair_b200._lib import TairError
