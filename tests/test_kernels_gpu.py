@@ -299,6 +299,65 @@ def test_blend_tiles_fixture_and_ragged_list(ops, golden):
     assert torch.equal(ops.blend_tiles(tl[:4].contiguous(), 2, 3, 64, 4 * oh, 4 * ow).cpu(), ref)
 
 
+def test_norms_full_size_invariances(ops):
+    """Normalisation properties at the sizes of a B=16 step: GroupNorm(a x + b_g) == GroupNorm(x) for a positive scale and
+    a per-group shift, LayerNorm(a x + b) == LayerNorm(x) for a per-row shift (both up to the bf16 rounding of the
+    transformed input), and every image of the batch equals that image normalised alone (bit for bit)."""
+    B, HW, C = 16, 4096, 320
+    x = (rn(B, HW, C, seed=21) * 1.5).bfloat16()
+    g, b = 1 + 0.1 * rn(C, seed=22), 0.1 * rn(C, seed=23)
+    y = ops.groupnorm(x, g, b, act=ops.ACT_SILU)
+    shift = rn(B, 1, 32, 1, seed=24).expand(B, HW, 32, C // 32).reshape(B, HW, C)
+    y2 = ops.groupnorm((x.float() * 2.0 + shift).bfloat16(), g, b, act=ops.ACT_SILU)
+    assert rel(y2, y) < 2e-2
+    assert torch.equal(y[5:6], ops.groupnorm(x[5:6].contiguous(), g, b, act=ops.ACT_SILU))
+    M, Cl = 151552, 256
+    r = rn(M, Cl, seed=25).bfloat16()
+    gl, bl = 1 + 0.1 * rn(Cl, seed=26), 0.1 * rn(Cl, seed=27)
+    z = ops.layernorm(r, gl, bl)
+    z2 = ops.layernorm((r.float() * 4.0 + rn(M, 1, seed=28)).bfloat16(), gl, bl)
+    assert rel(z2, z) < 2e-2
+    assert torch.equal(z[1000:1003], ops.layernorm(r[1000:1003].contiguous(), gl, bl))
+
+
+def test_msda_fused_full_size_is_linear_in_the_values(ops):
+    """Deformable attention at the TESTR encoder size (B=16, 9472 queries, 8 heads, 4 levels x 4 points) is linear in the
+    value tensor for fixed sampling offsets and attention logits: msda(v1 + v2) == msda(v1) + msda(v2) up to bf16."""
+    B, M, D = 16, 8, 32
+    shapes = [(16, 16), (32, 32), (64, 64), (64, 64)]
+    S = sum(h * w for h, w in shapes)
+    shp = torch.tensor(shapes, device="cuda", dtype=torch.long)
+    start = torch.cat([shp.new_zeros(1), (shp[:, 0] * shp[:, 1]).cumsum(0)[:-1]])
+    v1, v2 = rn(B, S, M, D, seed=31).bfloat16(), rn(B, S, M, D, seed=32).bfloat16()
+    proj = torch.cat([rn(B * S, M * 16 * 2, seed=33) * 2.0, rn(B * S, M * 16, seed=34)], 1).bfloat16().contiguous()
+    refs = []
+    for (h, w) in shapes:
+        ry, rx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device="cuda"), torch.linspace(0.5, w - 0.5, w, device="cuda"), indexing="ij")
+        refs.append(torch.stack((rx.reshape(-1) / w, ry.reshape(-1) / h), -1))
+    ref = torch.cat(refs, 0)[:, None, :].expand(S, 4, 2).contiguous()
+    kw = dict(B=B, Lq=S, n_heads=M, n_levels=4, n_points=4, q_per_ref=1, ref_shared=True)
+    o1 = ops.msda_fused(v1, shp, start, proj, ref, **kw).float()
+    o2 = ops.msda_fused(v2, shp, start, proj, ref, **kw).float()
+    o12 = ops.msda_fused((v1.float() + v2.float()).bfloat16(), shp, start, proj, ref, **kw).float()
+    assert rel(o12, o1 + o2) < 2e-2
+    assert torch.equal(ops.msda_fused(v1, shp, start, proj, ref, **kw).float(), o1)
+
+
+def test_blend_of_constant_tiles_is_constant_at_4k(ops):
+    """configs[4] geometry (3840 x 2160 LQ image, 35 x 20 = 700 tiles of 512^2, 15360 x 8640 output): blending tiles that
+    all hold the same value per channel gives exactly... that value up to one rounding of the weight normalisation, on
+    every output pixel (no uncovered pixel, no double-counted seam)."""
+    from oracle import tiles
+    oh, ow = 2160, 3840
+    n_h, n_w, _, _ = tiles.tile_grid(oh, ow)
+    assert n_h * n_w == 700
+    vals = torch.tensor([0.25, 0.5, 0.8125], device="cuda").view(1, 3, 1, 1)
+    tl = vals.expand(700, 3, 512, 512).contiguous()
+    out = ops.blend_tiles(tl, n_h, n_w, 64, 4 * oh, 4 * ow)
+    assert tuple(out.shape) == (1, 3, 4 * oh, 4 * ow)
+    assert (out - vals).abs().max().item() < 1e-6
+
+
 @pytest.mark.parametrize("M,C,N,act", [(300, 320, 960, "none"), (1000, 640, 640, "none"), (257, 64, 512, "geglu"),
                                        (4096, 1280, 10240, "geglu")])
 def test_layernorm_folded_into_gemm(cuda_lib, M, C, N, act):
