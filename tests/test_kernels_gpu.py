@@ -299,6 +299,36 @@ def test_blend_tiles_fixture_and_ragged_list(ops, golden):
     assert torch.equal(ops.blend_tiles(tl[:4].contiguous(), 2, 3, 64, 4 * oh, 4 * ow).cpu(), ref)
 
 
+def test_conv_and_attention_full_size_properties(ops):
+    """The two dominant kernels at the batch the bench runs (B=16).  3x3 conv 64^2 320->320: linear in its input, a shifted
+    image gives the shifted output away from the border (translation equivariance of the implicit-GEMM addressing), and
+    image 7 of the batch equals image 7 alone bit for bit.  Self-attention 4096^2, 5 heads: identical value rows are
+    reproduced, permuting the keys with their values changes nothing beyond bf16, and every (batch, head) is independent."""
+    B, H, C = 16, 64, 320
+    x1, x2 = rn(B, H, H, C, seed=41).bfloat16(), rn(B, H, H, C, seed=42).bfloat16()
+    w = rn(C, 9 * C, scale=(9 * C) ** -0.5, seed=43).bfloat16()
+    o1, o2 = ops.conv3x3(x1, w).float(), ops.conv3x3(x2, w).float()
+    o12 = ops.conv3x3((x1.float() + x2.float()).bfloat16(), w).float()
+    assert rel(o12, o1 + o2) < 2e-2
+    sh = torch.roll(x1, shifts=(3, 5), dims=(1, 2))
+    osh = ops.conv3x3(sh.contiguous(), w).float()
+    assert torch.equal(osh[:, 5:-2, 7:-2], torch.roll(o1, shifts=(3, 5), dims=(1, 2))[:, 5:-2, 7:-2])
+    assert torch.equal(ops.conv3x3(x1[7:8].contiguous(), w).float(), o1[7:8])
+    Hh, L = 5, 4096
+    E = Hh * 64
+    q, k, v = rn(B * L, E, scale=1.5, seed=44).bfloat16(), rn(B * L, E, scale=1.5, seed=45).bfloat16(), rn(B * L, E, seed=46).bfloat16()
+    out = ops.attention(q, k, v, B=B, H=Hh, Lq=L, Lk=L)
+    perm = torch.randperm(L, device="cuda", generator=torch.Generator(device="cuda").manual_seed(47))
+    kp = k.view(B, L, E)[:, perm].reshape(B * L, E).contiguous()
+    vp = v.view(B, L, E)[:, perm].reshape(B * L, E).contiguous()
+    assert rel(ops.attention(q, kp, vp, B=B, H=Hh, Lq=L, Lk=L), out) < BF16_TOL
+    vc = rn(1, E, seed=48).bfloat16().expand(B * L, E).contiguous()
+    assert rel(ops.attention(q, k, vc, B=B, H=Hh, Lq=L, Lk=L), vc) < BF16_TOL
+    one = ops.attention(q.view(B, L, E)[3].contiguous(), k.view(B, L, E)[3].contiguous(), v.view(B, L, E)[3].contiguous(),
+                        B=1, H=Hh, Lq=L, Lk=L)
+    assert torch.equal(one, out.view(B, L, E)[3])
+
+
 def test_norms_full_size_invariances(ops):
     """Normalisation properties at the sizes of a B=16 step: GroupNorm(a x + b_g) == GroupNorm(x) for a positive scale and
     a per-group shift, LayerNorm(a x + b) == LayerNorm(x) for a per-row shift (both up to the bf16 rounding of the
